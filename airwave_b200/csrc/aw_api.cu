@@ -1,0 +1,1105 @@
+// aw_api.cu — C ABI of libairwave_cuda.so: plan cache, HRIR filter banks, the batched engine
+// (frame adapter + convolution + EQ state machines) and the host<->device staging.
+//
+// Host-side control mirrors, per stream range, the objects the reference keeps per process:
+//   Segment   = RendererState (HRIRManager.swift:123-131): streams sharing one bank + FDL head
+//   EqMachine = EqualizerRuntimeEffect + ParametricEqualizerProcessor render-thread state
+//               (EqualizerRuntimeEffect.swift:5-78, ParametricEqualizerProcessor.swift:121-408)
+// All streams of an engine advance in lock-step, so adapter counters are per engine.
+// aw_engine_process* allocates nothing: every buffer, stream, event and table is created up front.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/airwave_cuda.h"
+#include "aw_internal.h"
+#include "aw_kernels.h"
+
+namespace aw {
+static thread_local std::string g_last_error;
+int set_error(int status, const std::string &message)
+{
+    g_last_error = message;
+    return status;
+}
+}  // namespace aw
+
+using namespace aw;
+
+#define AW_CUDA(call)                                                                                     \
+    do {                                                                                                  \
+        cudaError_t e_ = (call);                                                                          \
+        if (e_ != cudaSuccess) return set_error(AW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// ---- plan cache (FFTSetupManager.swift:41-69) ----------------------------------------------------
+std::mutex g_plan_mutex;
+std::map<std::pair<int, int>, float2 *> g_plans;   // (device, log2n) -> twiddles exp(-2*pi*i*k/N), k < N/2
+
+int get_plan(int device, int log2n, const float2 **out)
+{
+    if (log2n < 3 || log2n > 14) return set_error(AW_ERR_INVALID_ARGUMENT, "plan: log2n out of range [3, 14]");
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    auto it = g_plans.find({device, log2n});
+    if (it != g_plans.end()) { if (out) *out = it->second; return AW_OK; }
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(AW_ERR_CUDA, "plan: cudaSetDevice failed");
+    const int N = 1 << log2n, half = N / 2;
+    std::vector<float2> tw(half);
+    for (int k = 0; k < half; ++k) {
+        const double a = -2.0 * M_PI * (double)k / (double)N;
+        tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    float2 *d = nullptr;
+    AW_CUDA(cudaMalloc(&d, sizeof(float2) * half));
+    cudaError_t e = cudaMemcpy(d, tw.data(), sizeof(float2) * half, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { cudaFree(d); return set_error(AW_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e)); }
+    e = configure_kernels(log2n - 1);
+    if (e != cudaSuccess) { cudaFree(d); return set_error(AW_ERR_CUDA, std::string("configure_kernels: ") + cudaGetErrorString(e)); }
+    g_plans[{device, log2n}] = d;
+    if (out) *out = d;
+    return AW_OK;
+}
+
+}  // namespace
+
+// ---- opaque types ----------------------------------------------------------------------------------
+struct aw_bank {
+    int device = 0, S = 0, B = 0, log2m = 0, P = 0, taps = 0;
+    float4 *d_bank = nullptr;   // [S][P][B] {L.re, L.im, R.re, R.im}
+    float *d_ny = nullptr;      // [S][P][2]
+};
+
+namespace {
+
+struct Segment {
+    int first, count;
+    const aw_bank *bank;   // nullptr = passthrough
+    int head;              // fdlIndex (ConvolutionEngine.swift:39)
+};
+
+constexpr int kEqPool = 1024;   // ParametricEqualizerState objects alive per engine (slot 0 = shared unity)
+
+struct EqMachine {
+    int first = 0, count = 0;
+    bool hasProcessor = false;     // EqualizerRuntimeEffect.controlProcessor != nil
+    bool eqActive = false;         // AudioEffectGraph.equalizerActiveLock state
+    bool lockHeld = false;         // publication lock contended (testing)
+    bool resetRequested = false;
+    int published = -1, audioThreadTarget = -1, activeState = 0, transitionFrom = -1, transitionTo = -1;
+    int pendingTarget = -1, observedTarget = -1, pendingRetirement = -1, retired = -1;
+    int transitionFrame = 0;
+    int activeVoice = 0;           // z-state voice holding activeState's history
+};
+
+struct Staging {
+    float *d_in = nullptr, *d_out = nullptr;
+    cudaEvent_t in_ready = nullptr, compute_done = nullptr, out_done = nullptr;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct aw_engine {
+    aw_engine_config cfg{};
+    int n = 0, S = 0, B = 0, log2m = 0, maxFrames = 0, P_cap = 0, fifoCap = 0;
+    int macTile = 0;
+    const float2 *d_tw = nullptr;
+    float2 *d_fdl = nullptr;
+    float *d_fdl_ny = nullptr, *d_overlap = nullptr, *d_pending = nullptr, *d_fifo = nullptr;
+    float2 *d_acc = nullptr;
+    double *d_eq_z = nullptr;
+    EqProgram *d_eq_prog = nullptr;
+    Staging stage[2];
+    int nextStage = 0;
+    cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    std::vector<Segment> segments;
+    std::vector<EqMachine> machines;
+    // EQ state-object pool (host mirror of the programs resident on the device)
+    std::vector<int> eqRef;          // refcounts; 0 = free
+    std::vector<int> eqFilters;      // filter count per slot
+    std::vector<double> eqPreamp;    // preampLinear per slot
+    int transitionLength = 1;
+    // adapter counters (RealtimeAudioProcessor.swift:26-28)
+    int pendingCount = 0, fifoReadIndex = 0, fifoCount = 0;
+    unsigned long long launches = 0, blocks = 0, h2dBytes = 0, d2hBytes = 0;
+};
+
+namespace {
+
+#define AW_LAUNCH(e, call)                                                                                 \
+    do {                                                                                                   \
+        cudaError_t le_ = (call);                                                                          \
+        ++(e)->launches;                                                                                   \
+        if (le_ != cudaSuccess) return set_error(AW_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(le_)); \
+    } while (0)
+
+int check_range(const aw_engine *e, int first, int count)
+{
+    if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
+    if (first < 0 || count <= 0 || first + count > e->n) return set_error(AW_ERR_RANGE, "stream range outside [0, n_streams)");
+    return AW_OK;
+}
+
+// Splits the segment list so that [first, first+count) is covered by whole segments.
+void split_segments(aw_engine *e, int at)
+{
+    for (size_t i = 0; i < e->segments.size(); ++i) {
+        Segment &s = e->segments[i];
+        if (at > s.first && at < s.first + s.count) {
+            Segment tail = s;
+            tail.first = at;
+            tail.count = s.first + s.count - at;
+            s.count = at - s.first;
+            e->segments.insert(e->segments.begin() + i + 1, tail);
+            return;
+        }
+    }
+}
+
+void split_machines(aw_engine *e, int at);
+
+// ---- EQ state pool ---------------------------------------------------------------------------------
+void eq_retain(aw_engine *e, int slot) { if (slot > 0) ++e->eqRef[slot]; }
+void eq_release(aw_engine *e, int slot) { if (slot > 0 && e->eqRef[slot] > 0) --e->eqRef[slot]; }
+void eq_assign(aw_engine *e, int &dst, int slot)
+{
+    eq_retain(e, slot);
+    eq_release(e, dst);
+    dst = slot;
+}
+
+void split_machines(aw_engine *e, int at)
+{
+    for (size_t i = 0; i < e->machines.size(); ++i) {
+        EqMachine &m = e->machines[i];
+        if (at > m.first && at < m.first + m.count) {
+            EqMachine tail = m;
+            tail.first = at;
+            tail.count = m.first + m.count - at;
+            m.count = at - m.first;
+            int *refs[] = {&tail.published, &tail.audioThreadTarget, &tail.activeState, &tail.transitionFrom, &tail.transitionTo,
+                           &tail.pendingTarget, &tail.observedTarget, &tail.pendingRetirement, &tail.retired};
+            for (int *r : refs) eq_retain(e, *r);
+            e->machines.insert(e->machines.begin() + i + 1, tail);
+            return;
+        }
+    }
+}
+
+// ParametricEqualizerProcessor.prepare (ParametricEqualizerProcessor.swift:174-217): validates, designs the biquads and
+// uploads one immutable program.  Returns the pool slot (refcount 1) in *slot.
+int eq_prepare_state(aw_engine *e, double preampDB, const aw_eq_filter *filters, int n_filters, int *slot, int *bad_index,
+                     int *bad_reason)
+{
+    if (bad_index) *bad_index = -1;
+    if (bad_reason) *bad_reason = 0;
+    const double sampleRate = e->cfg.sample_rate;
+    if (!(std::isfinite(sampleRate) && sampleRate > 0)) return set_error(AW_ERR_EQ_INVALID_SAMPLE_RATE, "Sample rate must be finite and positive.");
+    if (n_filters < 0) { preampDB = 0; n_filters = 0; }   // definition == nil (:182,191)
+    if (!std::isfinite(preampDB)) return set_error(AW_ERR_EQ_NON_FINITE_PREAMP, "Preamp must produce a finite linear gain.");
+    const double preampLinear = std::pow(10.0, preampDB / 20.0);
+    if (!std::isfinite(preampLinear)) return set_error(AW_ERR_EQ_NON_FINITE_PREAMP, "Preamp must produce a finite linear gain.");
+    int enabled = 0;
+    for (int i = 0; i < n_filters; ++i) if (filters[i].enabled) ++enabled;
+    if (enabled > 64) {
+        if (bad_index) *bad_index = enabled;
+        return set_error(AW_ERR_EQ_TOO_MANY_FILTERS, "Equalizer supports at most 64 filters; received " + std::to_string(enabled) + ".");
+    }
+    EqProgram prog;
+    memset(&prog, 0, sizeof(prog));
+    prog.preamp_linear = preampLinear;
+    int k = 0;
+    for (int i = 0; i < n_filters; ++i) {
+        if (!filters[i].enabled) continue;
+        const int rc = aw_biquad_make(filters[i].type, filters[i].gain_db, filters[i].frequency_hz, filters[i].q, sampleRate, prog.coef[k]);
+        if (rc != AW_BIQUAD_OK) {
+            if (bad_index) *bad_index = k;
+            if (bad_reason) *bad_reason = rc;
+            static const char *reasons[] = {"", "Sample rate must be finite and positive.", "Frequency must be finite, positive, and below Nyquist.",
+                                            "Q must be finite and positive.", "Filter parameters must be finite.", "Filter coefficients must be finite."};
+            return set_error(AW_ERR_EQ_INVALID_FILTER, "Filter " + std::to_string(k + 1) + " is invalid: " + reasons[rc]);
+        }
+        ++k;
+    }
+    prog.n_filters = k;
+    int s = -1;
+    for (int i = 1; i < kEqPool; ++i) if (e->eqRef[i] == 0) { s = i; break; }
+    if (s < 0) return set_error(AW_ERR_OUT_OF_MEMORY, "equalizer state pool exhausted");
+    AW_CUDA(cudaMemcpyAsync(e->d_eq_prog + s, &prog, sizeof(prog), cudaMemcpyHostToDevice, e->stream));
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    e->eqRef[s] = 1;
+    e->eqFilters[s] = k;
+    e->eqPreamp[s] = preampLinear;
+    *slot = s;
+    return AW_OK;
+}
+
+// ---- render-thread half of ParametricEqualizerProcessor (:317-407), one instance per EqMachine --------
+int eq_begin_transition(aw_engine *e, EqMachine &m, int target)   // :354-359
+{
+    if (target == m.activeState) return AW_OK;
+    eq_assign(e, m.transitionFrom, m.activeState);
+    eq_assign(e, m.transitionTo, target);
+    m.transitionFrame = 0;
+    // the target state object starts with zero history: clear the voice it will run on
+    AW_LAUNCH(e, launch_eq_reset(e->d_eq_z, m.first, m.count, 1 << (1 - m.activeVoice), e->stream));
+    return AW_OK;
+}
+
+int eq_start_pending(aw_engine *e, EqMachine &m)
+{
+    if (m.pendingTarget >= 0) {
+        const int pending = m.pendingTarget;
+        eq_retain(e, pending);
+        eq_assign(e, m.pendingTarget, -1);
+        int rc = AW_OK;
+        if (pending != m.activeState) rc = eq_begin_transition(e, m, pending);
+        eq_release(e, pending);
+        return rc;
+    }
+    return AW_OK;
+}
+
+bool eq_retire(aw_engine *e, EqMachine &m, int state)   // :377-389
+{
+    if (m.pendingRetirement >= 0) return false;
+    if (m.retired < 0) { eq_assign(e, m.retired, state); return true; }
+    eq_assign(e, m.pendingRetirement, state);
+    return false;
+}
+
+int eq_finish_transition(aw_engine *e, EqMachine &m)   // :361-375
+{
+    if (m.transitionFrom < 0 || m.transitionTo < 0) return AW_OK;
+    const int from = m.transitionFrom;
+    eq_retain(e, from);
+    eq_assign(e, m.activeState, m.transitionTo);
+    m.activeVoice = 1 - m.activeVoice;
+    eq_assign(e, m.transitionFrom, -1);
+    eq_assign(e, m.transitionTo, -1);
+    m.transitionFrame = 0;
+    const bool ok = eq_retire(e, m, from);
+    eq_release(e, from);
+    if (!ok) return AW_OK;
+    return eq_start_pending(e, m);
+}
+
+int eq_observe_published_target(aw_engine *e, EqMachine &m)   // :317-339
+{
+    if (!m.lockHeld && m.published >= 0) eq_assign(e, m.audioThreadTarget, m.published);
+    const int target = m.audioThreadTarget;
+    if (target < 0 || target == m.observedTarget) return AW_OK;
+    eq_assign(e, m.observedTarget, target);
+    if (m.transitionTo >= 0) {
+        if (target != m.transitionTo) eq_assign(e, m.pendingTarget, target);
+    } else if (m.pendingRetirement >= 0) {
+        eq_assign(e, m.pendingTarget, target);
+    } else if (target != m.activeState) {
+        return eq_begin_transition(e, m, target);
+    }
+    return AW_OK;
+}
+
+int eq_flush_pending_retirement(aw_engine *e, EqMachine &m)   // :391-407
+{
+    if (m.pendingRetirement < 0 || m.retired >= 0) return AW_OK;
+    eq_assign(e, m.retired, m.pendingRetirement);
+    eq_assign(e, m.pendingRetirement, -1);
+    return eq_start_pending(e, m);
+}
+
+int eq_apply_pending_reset(aw_engine *e, EqMachine &m)   // :341-352
+{
+    if (!m.resetRequested) return AW_OK;
+    m.resetRequested = false;
+    AW_LAUNCH(e, launch_eq_reset(e->d_eq_z, m.first, m.count, 3, e->stream));
+    return AW_OK;
+}
+
+// ParametricEqualizerProcessor.process (:254-314) for one machine, in place on `io`.
+int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
+{
+    if (!m.eqActive || !m.hasProcessor) return AW_OK;   // graph bypass / EqualizerRuntimeEffect passthrough
+    int rc;
+    if ((rc = eq_observe_published_target(e, m)) != AW_OK) return rc;
+    if ((rc = eq_flush_pending_retirement(e, m)) != AW_OK) return rc;
+    if ((rc = eq_apply_pending_reset(e, m)) != AW_OK) return rc;
+    int offset = 0;
+    while (offset < frames) {
+        EqLaunch l;
+        memset(&l, 0, sizeof(l));
+        l.first_stream = m.first;
+        l.n_streams = m.count;
+        l.transition_length = e->transitionLength;
+        if (m.transitionFrom < 0 || m.transitionTo < 0) {
+            const int a = m.activeState;
+            if (e->eqFilters[a] == 0 && e->eqPreamp[a] == 1.0) return AW_OK;   // unity: Float(Double(x) * 1) == x
+            l.from = e->d_eq_prog + a;
+            l.to = nullptr;
+            l.from_voice = m.activeVoice;
+            l.to_voice = 1 - m.activeVoice;
+            l.seg_start = offset;
+            l.seg_len = frames - offset;
+            AW_LAUNCH(e, launch_eq(l, e->eqFilters[a], e->d_eq_z, io, e->stream));
+            return AW_OK;
+        }
+        const int remaining = e->transitionLength - m.transitionFrame;
+        const int segment = std::min(remaining, frames - offset);
+        l.from = e->d_eq_prog + m.transitionFrom;
+        l.to = e->d_eq_prog + m.transitionTo;
+        l.from_voice = m.activeVoice;
+        l.to_voice = 1 - m.activeVoice;
+        l.seg_start = offset;
+        l.seg_len = segment;
+        l.transition_frame = m.transitionFrame;
+        AW_LAUNCH(e, launch_eq(l, std::max(e->eqFilters[m.transitionFrom], e->eqFilters[m.transitionTo]), e->d_eq_z, io, e->stream));
+        m.transitionFrame += segment;
+        offset += segment;
+        if (m.transitionFrame == e->transitionLength && (rc = eq_finish_transition(e, m)) != AW_OK) return rc;
+    }
+    return AW_OK;
+}
+
+// ---- one block of UPOLS for every rendering segment ----------------------------------------------------
+int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap, StridedOut out)
+{
+    for (Segment &seg : e->segments) {
+        if (!seg.bank) continue;
+        const aw_bank *b = seg.bank;
+        seg.head -= 1;                                   // ConvolutionEngine.swift:256-259
+        if (seg.head < 0) seg.head += b->P;
+        BlockGeom g;
+        g.first_stream = seg.first;
+        g.n_streams = seg.count;
+        g.S = (e->cfg.flags & AW_ENGINE_LITERAL_STEREO) ? std::min(b->S, 2) : b->S;   // RealtimeAudioProcessor.swift:145
+        g.Se = e->S;
+        g.B = e->B;
+        g.log2m = e->log2m;
+        g.P = b->P;
+        g.P_cap = e->P_cap;
+        g.head = seg.head;
+        AW_LAUNCH(e, launch_input_rfft(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, e->d_tw, e->stream));
+        AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, b->d_bank, e->d_acc, e->macTile, e->stream));
+        AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, b->d_ny, out, e->d_tw, e->stream));
+    }
+    ++e->blocks;
+    return AW_OK;
+}
+
+bool any_rendering(const aw_engine *e)
+{
+    for (const Segment &s : e->segments) if (s.bank) return true;
+    return false;
+}
+
+// RealtimeAudioProcessor.process (RealtimeAudioProcessor.swift:77-119) + AudioEffectGraph routing (:179-246), device side.
+int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, bool dup_mono)
+{
+    if (frames <= 0) return AW_OK;                                              // :84
+    if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");   // :85
+    const int B = e->B;
+    // streams without a published renderer: passthrough copy (HRIRManager.swift:555-564)
+    for (const Segment &seg : e->segments)
+        if (!seg.bank) AW_LAUNCH(e, launch_passthrough(in, out, seg.first, seg.count, dup_mono ? 1 : e->S, frames, e->stream));
+    if (any_rendering(e)) {
+        const bool aligned = ((reinterpret_cast<uintptr_t>(in.ptr) & 7u) == 0) && (in.ss % 2 == 0) && (in.cs % 2 == 0);
+        const bool fast = e->pendingCount == 0 && e->fifoCount == 0 && frames % B == 0 && aligned && !dup_mono;
+        if (fast) {
+            // block-aligned fast path: same arithmetic, no pending/FIFO traffic (latency of one block is zero here
+            // exactly as in the reference: B frames in -> processPendingBlock -> B frames drained in the same call)
+            const int nb = frames / B;
+            StridedIn ov{e->d_overlap, (long long)e->S * B, (long long)B};
+            for (int b = 0; b < nb; ++b) {
+                StridedIn cur{in.ptr + (size_t)b * B, in.ss, in.cs};
+                StridedIn prev = b == 0 ? ov : StridedIn{in.ptr + (size_t)(b - 1) * B, in.ss, in.cs};
+                StridedOut o{out.ptr + (size_t)b * B, out.ss, out.cs, 0, 0};
+                const int rc = process_block(e, cur, prev, b == nb - 1, o);
+                if (rc != AW_OK) return rc;
+            }
+        } else {
+            int inputOffset = 0;
+            StridedIn pend{e->d_pending, (long long)e->S * B, (long long)B};
+            StridedIn ov{e->d_overlap, (long long)e->S * B, (long long)B};
+            while (inputOffset < frames) {                                       // :88-116
+                const int copyCount = std::min(B - e->pendingCount, frames - inputOffset);
+                AW_LAUNCH(e, launch_gather_pending(in, inputOffset, copyCount, e->d_pending, e->pendingCount, e->n, e->S, B,
+                                                   dup_mono ? 1 : 0, e->stream));
+                e->pendingCount += copyCount;
+                inputOffset += copyCount;
+                if (e->pendingCount == B) {
+                    const int writeIndex = (e->fifoReadIndex + e->fifoCount) % e->fifoCap;   // :167
+                    StridedOut o{e->d_fifo, (long long)2 * e->fifoCap, (long long)e->fifoCap, e->fifoCap, writeIndex};
+                    const int rc = process_block(e, pend, ov, true, o);
+                    if (rc != AW_OK) return rc;
+                    e->fifoCount += B;
+                    e->pendingCount = 0;
+                }
+            }
+            // drain (:174-190); passthrough streams were already written, so drain only rendering segments
+            for (const Segment &seg : e->segments) {
+                if (!seg.bank) continue;
+                StridedOut o{out.ptr + (size_t)seg.first * out.ss, out.ss, out.cs, 0, 0};
+                AW_LAUNCH(e, launch_drain_fifo(e->d_fifo + (size_t)seg.first * 2 * e->fifoCap, e->fifoCap, e->fifoReadIndex, e->fifoCount, o, 0,
+                                               frames, seg.count, e->stream));
+            }
+            const int drained = std::min(e->fifoCount, frames);
+            e->fifoReadIndex = (e->fifoReadIndex + drained) % e->fifoCap;
+            e->fifoCount -= drained;
+        }
+    }
+    // equalizer after spatial (AudioEffectGraph.swift:195-210), in place on the output
+    for (EqMachine &m : e->machines) {
+        const int rc = eq_process_machine(e, m, out, frames);
+        if (rc != AW_OK) return rc;
+    }
+    return AW_OK;
+}
+
+void free_engine(aw_engine *e)
+{
+    if (!e) return;
+    DeviceGuard guard(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->d_fdl); cudaFree(e->d_fdl_ny); cudaFree(e->d_overlap); cudaFree(e->d_pending); cudaFree(e->d_fifo);
+    cudaFree(e->d_acc); cudaFree(e->d_eq_z); cudaFree(e->d_eq_prog);
+    for (Staging &s : e->stage) {
+        cudaFree(s.d_in); cudaFree(s.d_out);
+        if (s.in_ready) cudaEventDestroy(s.in_ready);
+        if (s.compute_done) cudaEventDestroy(s.compute_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->h2d) cudaStreamDestroy(e->h2d);
+    if (e->d2h) cudaStreamDestroy(e->d2h);
+    delete e;
+}
+
+int alloc_fdl(aw_engine *e, int P_cap)
+{
+    const size_t rows = (size_t)e->n * e->S * P_cap;
+    AW_CUDA(cudaMalloc(&e->d_fdl, rows * e->B * sizeof(float2)));
+    AW_CUDA(cudaMalloc(&e->d_fdl_ny, rows * sizeof(float)));
+    AW_CUDA(cudaMemsetAsync(e->d_fdl, 0, rows * e->B * sizeof(float2), e->stream));
+    AW_CUDA(cudaMemsetAsync(e->d_fdl_ny, 0, rows * sizeof(float), e->stream));
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    e->P_cap = P_cap;
+    return AW_OK;
+}
+
+int clear_spatial_state(aw_engine *e, int first, int count)
+{
+    if (e->d_fdl) {
+        const size_t per = (size_t)e->S * e->P_cap;
+        AW_CUDA(cudaMemsetAsync(e->d_fdl + (size_t)first * per * e->B, 0, (size_t)count * per * e->B * sizeof(float2), e->stream));
+        AW_CUDA(cudaMemsetAsync(e->d_fdl_ny + (size_t)first * per, 0, (size_t)count * per * sizeof(float), e->stream));
+    }
+    AW_CUDA(cudaMemsetAsync(e->d_overlap + (size_t)first * e->S * e->B, 0, (size_t)count * e->S * e->B * sizeof(float), e->stream));
+    return AW_OK;
+}
+
+}  // namespace
+
+// ---- library / device ----------------------------------------------------------------------------------
+extern "C" const char *aw_version(void) { return "airwave-b200 0.1 (sm_100a)"; }
+
+extern "C" const char *aw_status_string(int status)
+{
+    switch (status) {
+    case AW_OK: return "ok";
+    case AW_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case AW_ERR_CUDA: return "CUDA error";
+    case AW_ERR_OUT_OF_MEMORY: return "out of memory";
+    case AW_ERR_INVALID_BLOCK_SIZE: return "block size must be a power of two in [4, 8192]";
+    case AW_ERR_FRAME_COUNT: return "frameCount exceeds maxFramesPerCallback";
+    case AW_ERR_CHANNEL_MAPPING: return "HRIR channel mapping out of range";
+    case AW_ERR_NO_RENDERERS: return "no valid renderers created";
+    case AW_ERR_RANGE: return "stream range out of bounds";
+    case AW_ERR_MISMATCH: return "bank and engine do not match";
+    case AW_ERR_UNSUPPORTED: return "unsupported";
+    case AW_ERR_RESAMPLE_DOWN: return "down-sampling is undefined in the reference resampler";
+    case AW_ERR_NOT_READY: return "not ready";
+    case AW_ERR_EQ_INVALID_SAMPLE_RATE: return "invalid sample rate";
+    case AW_ERR_EQ_NON_FINITE_PREAMP: return "non-finite preamp";
+    case AW_ERR_EQ_TOO_MANY_FILTERS: return "too many filters";
+    case AW_ERR_EQ_INVALID_FILTER: return "invalid filter";
+    case AW_ERR_WAV_READ: return "WAV read error";
+    case AW_ERR_WAV_CHANNEL_COUNT: return "invalid WAV channel count";
+    case AW_ERR_WAV_EMPTY: return "empty WAV file";
+    case AW_ERR_WAV_UNSUPPORTED_FORMAT: return "unsupported WAV format";
+    case AW_ERR_EQ_PARSE: return "equalizer parse error";
+    default: return "unknown status";
+    }
+}
+
+extern "C" const char *aw_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int aw_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+extern "C" int aw_plan_prepare(int device, int log2n) { return get_plan(device, log2n, nullptr); }
+
+extern "C" int aw_plan_cache_stats(int device, int *count, int *sizes, int capacity)
+{
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
+    int c = 0;
+    for (auto &kv : g_plans) {
+        if (kv.first.first != device) continue;
+        if (sizes && c < capacity) sizes[c] = 1 << kv.first.second;
+        ++c;
+    }
+    if (count) *count = c;
+    return AW_OK;
+}
+
+extern "C" void *aw_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+extern "C" void aw_host_free(void *ptr) { if (ptr) cudaFreeHost(ptr); }
+
+// ---- resampler -------------------------------------------------------------------------------------------
+extern "C" int aw_resample_output_count(int count, double from_rate, double to_rate)
+{
+    if (std::fabs(from_rate - to_rate) < 0.01) return count;     // Resampler.swift:33
+    const double stride = from_rate / to_rate;                   // :38
+    return (int)((double)count / stride);                        // :39
+}
+
+extern "C" int aw_resample(int device, const float *input, int count, double from_rate, double to_rate, float *output, int capacity,
+                           int *written)
+{
+    if (!input || !output || count <= 0) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_resample: bad argument");
+    const int outCount = aw_resample_output_count(count, from_rate, to_rate);
+    if (written) *written = outCount > 0 ? outCount : 0;
+    if (std::fabs(from_rate - to_rate) < 0.01) {
+        if (capacity < count) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_resample: capacity too small");
+        memcpy(output, input, sizeof(float) * count);
+        return AW_OK;
+    }
+    if (outCount <= 0) return AW_OK;                             // :41
+    if (outCount < count) return set_error(AW_ERR_RESAMPLE_DOWN, "down-sampling reads past the control vector in the reference");
+    if (capacity < outCount) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_resample: capacity too small");
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(AW_ERR_CUDA, "cudaSetDevice failed");
+    float *d_in = nullptr, *d_out = nullptr;
+    AW_CUDA(cudaMalloc(&d_in, sizeof(float) * count));
+    cudaError_t e = cudaMalloc(&d_out, sizeof(float) * outCount);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, input, sizeof(float) * count, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_resample_vgenp(d_in, 1, count, (float)(from_rate / to_rate), d_out, outCount, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(output, d_out, sizeof(float) * outCount, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return set_error(AW_ERR_CUDA, std::string("aw_resample: ") + cudaGetErrorString(e));
+    return AW_OK;
+}
+
+// ---- bank -------------------------------------------------------------------------------------------------
+extern "C" int aw_bank_create(int device, const float *pcm, int channels, int frames, double src_rate, double dst_rate,
+                              const int *left_idx, const int *right_idx, int n_speakers, int block, aw_bank **out)
+{
+    if (!out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_bank_create: null out");
+    *out = nullptr;
+    if (!pcm || !left_idx || !right_idx || channels <= 0 || frames <= 0 || n_speakers <= 0)
+        return set_error(AW_ERR_INVALID_ARGUMENT, "aw_bank_create: bad argument");
+    if (!is_pow2(block) || block < 4 || block > 8192) return set_error(AW_ERR_INVALID_BLOCK_SIZE, "ConvolutionEngine: block size must be a power of two in [4, 8192]");
+    // build loop of HRIRManager.activatePreset (:366-418): skip unmapped speakers, validate indices
+    std::vector<int> l, r;
+    for (int i = 0; i < n_speakers; ++i) {
+        if (left_idx[i] < 0 || right_idx[i] < 0) continue;                      // getIndices == nil -> continue (:370-372)
+        if (!(left_idx[i] < channels && right_idx[i] < channels))               // :375-379
+            return set_error(AW_ERR_CHANNEL_MAPPING, "HRIR indices (" + std::to_string(left_idx[i]) + ", " + std::to_string(right_idx[i]) +
+                                                         ") out of range for " + std::to_string(channels) + " channels");
+        l.push_back(left_idx[i]);
+        r.push_back(right_idx[i]);
+    }
+    const int S = (int)l.size();
+    if (S == 0) return set_error(AW_ERR_NO_RENDERERS, "No valid renderers created");   // :420-422
+    const bool resample = std::fabs(src_rate - dst_rate) > 0.01;                // :389
+    int taps = frames;
+    if (resample) {
+        taps = aw_resample_output_count(frames, src_rate, dst_rate);
+        if (taps <= 0) return set_error(AW_ERR_INVALID_ARGUMENT, "resampled impulse response is empty");
+        if (taps < frames) return set_error(AW_ERR_RESAMPLE_DOWN, "down-sampling reads past the control vector in the reference");
+    }
+    DeviceGuard guard(device);
+    if (!guard.ok) return set_error(AW_ERR_CUDA, "cudaSetDevice failed (no CUDA device? there is no CPU fallback)");
+    const int log2m = ilog2(block);
+    const float2 *tw = nullptr;
+    int rc = get_plan(device, log2m + 1, &tw);
+    if (rc != AW_OK) return rc;
+    std::vector<float> ir((size_t)S * 2 * frames);
+    for (int s = 0; s < S; ++s) {
+        memcpy(&ir[((size_t)s * 2 + 0) * frames], pcm + (size_t)l[s] * frames, sizeof(float) * frames);
+        memcpy(&ir[((size_t)s * 2 + 1) * frames], pcm + (size_t)r[s] * frames, sizeof(float) * frames);
+    }
+    aw_bank *b = new aw_bank();
+    b->device = device; b->S = S; b->B = block; b->log2m = log2m; b->taps = taps;
+    b->P = (taps + block - 1) / block;                                          // ConvolutionEngine.swift:93
+    float *d_ir = nullptr, *d_rs = nullptr;
+    cudaError_t e = cudaMalloc(&d_ir, sizeof(float) * ir.size());
+    if (e == cudaSuccess) e = cudaMemcpy(d_ir, ir.data(), sizeof(float) * ir.size(), cudaMemcpyHostToDevice);
+    const float *d_src = d_ir;
+    if (e == cudaSuccess && resample) {
+        e = cudaMalloc(&d_rs, sizeof(float) * (size_t)S * 2 * taps);
+        if (e == cudaSuccess) e = launch_resample_vgenp(d_ir, S * 2, frames, (float)(src_rate / dst_rate), d_rs, taps, 0);
+        d_src = d_rs;
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_bank, sizeof(float4) * (size_t)S * b->P * block);
+    if (e == cudaSuccess) e = cudaMalloc(&b->d_ny, sizeof(float) * (size_t)S * b->P * 2);
+    if (e == cudaSuccess) e = launch_bank_build(d_src, S, taps, block, log2m, b->P, b->d_bank, b->d_ny, tw, 0);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaFree(d_ir);
+    cudaFree(d_rs);
+    if (e != cudaSuccess) {
+        cudaFree(b->d_bank); cudaFree(b->d_ny);
+        delete b;
+        return set_error(e == cudaErrorMemoryAllocation ? AW_ERR_OUT_OF_MEMORY : AW_ERR_CUDA, std::string("aw_bank_create: ") + cudaGetErrorString(e));
+    }
+    *out = b;
+    return AW_OK;
+}
+
+extern "C" int aw_bank_create_from_wav(int device, const aw_wav *wav, double dst_rate, int layout, int block, aw_bank **out)
+{
+    if (!wav || !out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_bank_create_from_wav: null argument");
+    int speakers[16], l[16], r[16];
+    const int n = aw_layout_speakers(layout, speakers, 16);
+    if (n == 0) return set_error(AW_ERR_INVALID_ARGUMENT, "unknown input layout");
+    aw_hesuvi_map(wav->channels, speakers, n, l, r);
+    return aw_bank_create(device, wav->data.data(), wav->channels, wav->frames, wav->sample_rate, dst_rate, l, r, n, block, out);
+}
+
+extern "C" int aw_bank_info(const aw_bank *bank, int *n_speakers, int *block, int *partitions, int *taps)
+{
+    if (!bank) return set_error(AW_ERR_INVALID_ARGUMENT, "null bank");
+    if (n_speakers) *n_speakers = bank->S;
+    if (block) *block = bank->B;
+    if (partitions) *partitions = bank->P;
+    if (taps) *taps = bank->taps;
+    return AW_OK;
+}
+
+extern "C" int aw_bank_read(const aw_bank *bank, float *spectrum, float *nyquist)
+{
+    if (!bank) return set_error(AW_ERR_INVALID_ARGUMENT, "null bank");
+    DeviceGuard guard(bank->device);
+    if (spectrum) AW_CUDA(cudaMemcpy(spectrum, bank->d_bank, sizeof(float4) * (size_t)bank->S * bank->P * bank->B, cudaMemcpyDeviceToHost));
+    if (nyquist) AW_CUDA(cudaMemcpy(nyquist, bank->d_ny, sizeof(float) * (size_t)bank->S * bank->P * 2, cudaMemcpyDeviceToHost));
+    return AW_OK;
+}
+
+extern "C" void aw_bank_destroy(aw_bank *bank)
+{
+    if (!bank) return;
+    DeviceGuard guard(bank->device);
+    cudaFree(bank->d_bank);
+    cudaFree(bank->d_ny);
+    delete bank;
+}
+
+// ---- engine -------------------------------------------------------------------------------------------------
+extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
+{
+    if (!out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_create: null out");
+    *out = nullptr;
+    if (!config) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_create: null config");
+    if (config->n_streams <= 0 || config->n_speakers <= 0 || config->n_speakers > 64)
+        return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_create: n_streams and n_speakers must be positive");
+    if (!is_pow2(config->block) || config->block < 4 || config->block > 8192)
+        return set_error(AW_ERR_INVALID_BLOCK_SIZE, "block size must be a power of two in [4, 8192]");
+    const int maxFrames = config->max_frames_per_call > 0 ? config->max_frames_per_call : 4096;
+    DeviceGuard guard(config->device);
+    if (!guard.ok) return set_error(AW_ERR_CUDA, "cudaSetDevice failed (no CUDA device? there is no CPU fallback)");
+    aw_engine *e = new aw_engine();
+    e->cfg = *config;
+    e->n = config->n_streams; e->S = config->n_speakers; e->B = config->block; e->log2m = ilog2(config->block);
+    e->maxFrames = maxFrames;
+    e->fifoCap = maxFrames + e->B;                                              // RealtimeAudioProcessor.swift:41
+    int rc = get_plan(config->device, e->log2m + 1, &e->d_tw);
+    if (rc != AW_OK) { delete e; return rc; }
+    auto fail = [&](int status) { free_engine(e); return status; };
+#define AW_TRY(call)                                                                                       \
+    do {                                                                                                   \
+        cudaError_t te_ = (call);                                                                          \
+        if (te_ != cudaSuccess)                                                                            \
+            return fail(set_error(te_ == cudaErrorMemoryAllocation ? AW_ERR_OUT_OF_MEMORY : AW_ERR_CUDA,   \
+                                  std::string(#call) + ": " + cudaGetErrorString(te_)));                  \
+    } while (0)
+    AW_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    AW_TRY(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
+    AW_TRY(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
+    const size_t n = e->n, S = e->S, B = e->B;
+    AW_TRY(cudaMalloc(&e->d_overlap, n * S * B * sizeof(float)));
+    AW_TRY(cudaMalloc(&e->d_pending, n * S * B * sizeof(float)));
+    AW_TRY(cudaMalloc(&e->d_fifo, n * 2 * e->fifoCap * sizeof(float)));
+    AW_TRY(cudaMalloc(&e->d_acc, n * 2 * B * sizeof(float2)));
+    AW_TRY(cudaMalloc(&e->d_eq_z, n * 2 * 2 * 64 * 2 * sizeof(double)));
+    AW_TRY(cudaMalloc(&e->d_eq_prog, sizeof(EqProgram) * kEqPool));
+    AW_TRY(cudaMemsetAsync(e->d_overlap, 0, n * S * B * sizeof(float), e->stream));
+    AW_TRY(cudaMemsetAsync(e->d_pending, 0, n * S * B * sizeof(float), e->stream));
+    AW_TRY(cudaMemsetAsync(e->d_fifo, 0, n * 2 * e->fifoCap * sizeof(float), e->stream));
+    AW_TRY(cudaMemsetAsync(e->d_eq_z, 0, n * 2 * 2 * 64 * 2 * sizeof(double), e->stream));
+    AW_TRY(cudaMemsetAsync(e->d_eq_prog, 0, sizeof(EqProgram) * kEqPool, e->stream));
+    const int sets = (config->flags & AW_ENGINE_PIPELINED) ? 2 : 1;
+    for (int i = 0; i < sets; ++i) {
+        AW_TRY(cudaMalloc(&e->stage[i].d_in, n * S * maxFrames * sizeof(float)));
+        AW_TRY(cudaMalloc(&e->stage[i].d_out, n * 2 * maxFrames * sizeof(float)));
+        AW_TRY(cudaEventCreateWithFlags(&e->stage[i].in_ready, cudaEventDisableTiming));
+        AW_TRY(cudaEventCreateWithFlags(&e->stage[i].compute_done, cudaEventDisableTiming));
+        AW_TRY(cudaEventCreateWithFlags(&e->stage[i].out_done, cudaEventDisableTiming));
+    }
+    // unity program in slot 0 (ParametricEqualizerProcessor.unityState, :128,158)
+    EqProgram unity;
+    memset(&unity, 0, sizeof(unity));
+    unity.preamp_linear = 1.0;
+    AW_TRY(cudaMemcpyAsync(e->d_eq_prog, &unity, sizeof(unity), cudaMemcpyHostToDevice, e->stream));
+    AW_TRY(cudaStreamSynchronize(e->stream));
+    e->eqRef.assign(kEqPool, 0);
+    e->eqFilters.assign(kEqPool, 0);
+    e->eqPreamp.assign(kEqPool, 1.0);
+    e->eqRef[0] = 1 << 30;
+    const long tl = std::lround(config->sample_rate * 0.020);                   // ParametricEqualizerProcessor.swift:160
+    e->transitionLength = tl < 1 ? 1 : (int)tl;
+    e->segments.reserve(256);
+    e->machines.reserve(256);
+    e->segments.push_back(Segment{0, e->n, nullptr, 0});
+    EqMachine m;
+    m.first = 0; m.count = e->n;
+    e->machines.push_back(m);
+    const char *tile_env = getenv("AW_MAC_TILE");
+    e->macTile = tile_env ? atoi(tile_env) : 0;
+    if (!(e->macTile == 1 || e->macTile == 2 || e->macTile == 4 || e->macTile == 8))
+        e->macTile = e->n >= 2048 ? 4 : (e->n >= 512 ? 2 : 1);
+    if (config->max_partitions > 0) {
+        rc = alloc_fdl(e, config->max_partitions);
+        if (rc != AW_OK) return fail(rc);
+    }
+#undef AW_TRY
+    *out = e;
+    return AW_OK;
+}
+
+extern "C" void aw_engine_destroy(aw_engine *engine) { free_engine(engine); }
+
+extern "C" int aw_engine_set_bank(aw_engine *e, int first, int count, const aw_bank *bank)
+{
+    int rc = check_range(e, first, count);
+    if (rc != AW_OK) return rc;
+    DeviceGuard guard(e->cfg.device);
+    if (bank) {
+        if (bank->device != e->cfg.device || bank->B != e->B) return set_error(AW_ERR_MISMATCH, "bank device/block size differ from the engine's");
+        if (bank->S > e->S) return set_error(AW_ERR_MISMATCH, "bank has more speakers than the engine has input channels");
+        if (!e->d_fdl) { if ((rc = alloc_fdl(e, bank->P)) != AW_OK) return rc; }
+        if (bank->P > e->P_cap) return set_error(AW_ERR_MISMATCH, "bank has more partitions than the engine's max_partitions");
+    }
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    split_segments(e, first);
+    split_segments(e, first + count);
+    for (Segment &s : e->segments) {
+        if (s.first >= first && s.first + s.count <= first + count) { s.bank = bank; s.head = 0; }
+    }
+    // merge neighbours that ended up identical (same bank, same head)
+    for (size_t i = 0; i + 1 < e->segments.size();) {
+        Segment &a = e->segments[i], &b = e->segments[i + 1];
+        if (a.bank == b.bank && a.head == b.head) { a.count += b.count; e->segments.erase(e->segments.begin() + i + 1); }
+        else ++i;
+    }
+    if ((rc = clear_spatial_state(e, first, count)) != AW_OK) return rc;        // fresh engines: zero overlap + FDL
+    if (first == 0 && count == e->n) {                                          // new RealtimeAudioProcessor: empty FIFO
+        e->pendingCount = 0; e->fifoReadIndex = 0; e->fifoCount = 0;
+        AW_CUDA(cudaMemsetAsync(e->d_pending, 0, (size_t)e->n * e->S * e->B * sizeof(float), e->stream));
+        AW_CUDA(cudaMemsetAsync(e->d_fifo, 0, (size_t)e->n * 2 * e->fifoCap * sizeof(float), e->stream));
+    }
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    return AW_OK;
+}
+
+namespace {
+
+enum EqMode { kEqPrepare, kEqUpdate, kEqSetTarget, kEqInstall };
+
+int eq_control(aw_engine *e, int first, int count, double preamp_db, const aw_eq_filter *filters, int n_filters, EqMode mode,
+               bool drain, int *bad_index, int *bad_reason)
+{
+    int rc = check_range(e, first, count);
+    if (rc != AW_OK) return rc;
+    if (n_filters > 0 && !filters) return set_error(AW_ERR_INVALID_ARGUMENT, "null filters");
+    DeviceGuard guard(e->cfg.device);
+    split_machines(e, first);
+    split_machines(e, first + count);
+    if (mode == kEqUpdate) {
+        for (EqMachine &m : e->machines)
+            if (m.first >= first && m.first + m.count <= first + count && !m.hasProcessor)
+                return set_error(AW_ERR_NOT_READY, "Equalizer has not been prepared for an output.");   // EqualizerRuntimeEffect.swift:37-39
+    }
+    int slot = -1;
+    std::string message;
+    int status = eq_prepare_state(e, preamp_db, filters, n_filters, &slot, bad_index, bad_reason);
+    if (status != AW_OK) {
+        message = g_last_error;
+        if (status == AW_ERR_OUT_OF_MEMORY || status == AW_ERR_CUDA) return status;
+        if (mode == kEqSetTarget || mode == kEqInstall) return status;          // bare setTarget / prepare just throws
+        int unused_i, unused_r;
+        rc = eq_prepare_state(e, 0, nullptr, -1, &slot, &unused_i, &unused_r);  // try? processor.setTarget(definition: nil)
+        if (rc != AW_OK) return rc;
+    }
+    for (EqMachine &m : e->machines) {
+        if (!(m.first >= first && m.first + m.count <= first + count)) continue;
+        m.hasProcessor = true;
+        if (mode == kEqInstall) {   // use the state object directly: active, zero history, no transition
+            eq_assign(e, m.activeState, slot);
+            eq_assign(e, m.transitionFrom, -1);
+            eq_assign(e, m.transitionTo, -1);
+            eq_assign(e, m.pendingTarget, -1);
+            eq_assign(e, m.published, slot);
+            eq_assign(e, m.audioThreadTarget, slot);
+            eq_assign(e, m.observedTarget, slot);
+            m.transitionFrame = 0;
+            m.eqActive = true;
+            cudaError_t ze = launch_eq_reset(e->d_eq_z, m.first, m.count, 3, e->stream);
+            ++e->launches;
+            if (ze != cudaSuccess) return set_error(AW_ERR_CUDA, std::string("launch_eq_reset: ") + cudaGetErrorString(ze));
+            continue;
+        }
+        eq_assign(e, m.published, slot);                                        // publish (:219-226)
+        if (drain) eq_assign(e, m.retired, -1);                                 // drainRetiredStates (:247-251)
+        if (mode == kEqPrepare) m.eqActive = (status == AW_OK) && n_filters >= 0;   // AudioEffectGraph.swift:104-106,115-117
+        else if (mode == kEqUpdate) m.eqActive = true;                          // :150-152,159-161
+    }
+    eq_release(e, slot);   // the machines now hold the references
+    if (status != AW_OK) return set_error(status, message);
+    return AW_OK;
+}
+
+}  // namespace
+
+extern "C" int aw_engine_eq_prepare(aw_engine *e, int first, int count, double preamp_db, const aw_eq_filter *filters, int n_filters,
+                                    int *bad_index, int *bad_reason)
+{
+    return eq_control(e, first, count, preamp_db, filters, n_filters, kEqPrepare, true, bad_index, bad_reason);
+}
+
+extern "C" int aw_engine_eq_update(aw_engine *e, int first, int count, double preamp_db, const aw_eq_filter *filters, int n_filters,
+                                   int *bad_index, int *bad_reason)
+{
+    return eq_control(e, first, count, preamp_db, filters, n_filters, kEqUpdate, true, bad_index, bad_reason);
+}
+
+extern "C" int aw_engine_eq_set_target(aw_engine *e, int first, int count, double preamp_db, const aw_eq_filter *filters, int n_filters,
+                                       int drain_retired, int *bad_index, int *bad_reason)
+{
+    return eq_control(e, first, count, preamp_db, filters, n_filters, kEqSetTarget, drain_retired != 0, bad_index, bad_reason);
+}
+
+extern "C" int aw_engine_eq_install_state(aw_engine *e, int first, int count, double preamp_db, const aw_eq_filter *filters, int n_filters,
+                                          int *bad_index, int *bad_reason)
+{
+    return eq_control(e, first, count, preamp_db, filters, n_filters, kEqInstall, false, bad_index, bad_reason);
+}
+
+extern "C" int aw_engine_eq_drain_retired(aw_engine *e, int first, int count)
+{
+    int rc = check_range(e, first, count);
+    if (rc != AW_OK) return rc;
+    split_machines(e, first);
+    split_machines(e, first + count);
+    for (EqMachine &m : e->machines)
+        if (m.first >= first && m.first + m.count <= first + count) eq_assign(e, m.retired, -1);
+    return AW_OK;
+}
+
+extern "C" int aw_engine_eq_active(aw_engine *e, int first, int count, int active)
+{
+    int rc = check_range(e, first, count);
+    if (rc != AW_OK) return rc;
+    split_machines(e, first);
+    split_machines(e, first + count);
+    for (EqMachine &m : e->machines)
+        if (m.first >= first && m.first + m.count <= first + count) m.eqActive = active != 0;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_eq_hold_publication(aw_engine *e, int first, int count, int held)
+{
+    int rc = check_range(e, first, count);
+    if (rc != AW_OK) return rc;
+    split_machines(e, first);
+    split_machines(e, first + count);
+    for (EqMachine &m : e->machines)
+        if (m.first >= first && m.first + m.count <= first + count) m.lockHeld = held != 0;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_process_device(aw_engine *e, const float *in, long long in_stream_stride, long long in_channel_stride,
+                                        float *out, long long out_stream_stride, long long out_channel_stride, int frames)
+{
+    if (!e || !in || !out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_process_device: null argument");
+    DeviceGuard guard(e->cfg.device);
+    return process_device_impl(e, StridedIn{in, in_stream_stride, in_channel_stride},
+                               StridedOut{out, out_stream_stride, out_channel_stride, 0, 0}, frames, false);
+}
+
+extern "C" int aw_engine_process(aw_engine *e, const float *in, float *out, int frames)
+{
+    if (!e || !in || !out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_process: null argument");
+    if (frames <= 0) return AW_OK;
+    if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");
+    DeviceGuard guard(e->cfg.device);
+    Staging &s = e->stage[0];
+    const size_t inBytes = (size_t)e->n * e->S * frames * sizeof(float), outBytes = (size_t)e->n * 2 * frames * sizeof(float);
+    AW_CUDA(cudaMemcpyAsync(s.d_in, in, inBytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = process_device_impl(e, StridedIn{s.d_in, (long long)e->S * frames, (long long)frames},
+                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
+    if (rc != AW_OK) return rc;
+    AW_CUDA(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, e->stream));
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    e->h2dBytes += inBytes;
+    e->d2hBytes += outBytes;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_process_stereo(aw_engine *e, const float *input_left, const float *input_right, float *output_left,
+                                        float *output_right, int frames)
+{
+    if (!e || !input_left || !output_left || !output_right) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_process_stereo: null argument");
+    if (e->n != 1 || e->S > 2) return set_error(AW_ERR_UNSUPPORTED, "aw_engine_process_stereo needs n_streams == 1 and n_speakers <= 2");
+    if (frames <= 0) return AW_OK;
+    if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");
+    DeviceGuard guard(e->cfg.device);
+    Staging &s = e->stage[0];
+    const size_t bytes = (size_t)frames * sizeof(float);
+    AW_CUDA(cudaMemcpyAsync(s.d_in, input_left, bytes, cudaMemcpyHostToDevice, e->stream));
+    const bool dup = input_right == nullptr;
+    if (e->S == 2 && !dup) AW_CUDA(cudaMemcpyAsync(s.d_in + frames, input_right, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = process_device_impl(e, StridedIn{s.d_in, (long long)e->S * frames, (long long)frames},
+                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, dup && e->S == 2);
+    if (rc != AW_OK) return rc;
+    // left first, right second: with aliased outputs the right channel wins, as in RealtimeAudioProcessor.swift:181-182
+    AW_CUDA(cudaMemcpyAsync(output_left, s.d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    AW_CUDA(cudaMemcpyAsync(output_right, s.d_out + frames, bytes, cudaMemcpyDeviceToHost, e->stream));
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    e->h2dBytes += bytes * ((e->S == 2 && !dup) ? 2 : 1);
+    e->d2hBytes += 2 * bytes;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_submit(aw_engine *e, const float *in, float *out, int frames)
+{
+    if (!e || !in || !out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_submit: null argument");
+    if (!(e->cfg.flags & AW_ENGINE_PIPELINED)) return set_error(AW_ERR_UNSUPPORTED, "engine was not created with AW_ENGINE_PIPELINED");
+    if (frames <= 0) return AW_OK;
+    if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");
+    DeviceGuard guard(e->cfg.device);
+    Staging &s = e->stage[e->nextStage];
+    e->nextStage ^= 1;
+    const size_t inBytes = (size_t)e->n * e->S * frames * sizeof(float), outBytes = (size_t)e->n * 2 * frames * sizeof(float);
+    // staging set reuse: its previous input must have been consumed, its previous output copied out
+    if (s.busy) {
+        AW_CUDA(cudaStreamWaitEvent(e->h2d, s.compute_done, 0));
+        AW_CUDA(cudaStreamWaitEvent(e->stream, s.out_done, 0));
+    }
+    AW_CUDA(cudaMemcpyAsync(s.d_in, in, inBytes, cudaMemcpyHostToDevice, e->h2d));
+    AW_CUDA(cudaEventRecord(s.in_ready, e->h2d));
+    AW_CUDA(cudaStreamWaitEvent(e->stream, s.in_ready, 0));
+    const int rc = process_device_impl(e, StridedIn{s.d_in, (long long)e->S * frames, (long long)frames},
+                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
+    if (rc != AW_OK) return rc;
+    AW_CUDA(cudaEventRecord(s.compute_done, e->stream));
+    AW_CUDA(cudaStreamWaitEvent(e->d2h, s.compute_done, 0));
+    AW_CUDA(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, e->d2h));
+    AW_CUDA(cudaEventRecord(s.out_done, e->d2h));
+    s.busy = true;
+    e->h2dBytes += inBytes;
+    e->d2hBytes += outBytes;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_wait(aw_engine *e)
+{
+    if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
+    DeviceGuard guard(e->cfg.device);
+    AW_CUDA(cudaStreamSynchronize(e->h2d));
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    AW_CUDA(cudaStreamSynchronize(e->d2h));
+    return AW_OK;
+}
+
+extern "C" int aw_engine_reset(aw_engine *e, int first, int count, int what)
+{
+    int rc = check_range(e, first, count);
+    if (rc != AW_OK) return rc;
+    DeviceGuard guard(e->cfg.device);
+    if (what & AW_RESET_SPATIAL) {
+        // RealtimeAudioProcessor.reset (:121-139): engines reset (overlap, FDL, fdlIndex) + pending/FIFO cleared
+        split_segments(e, first);
+        split_segments(e, first + count);
+        for (Segment &s : e->segments)
+            if (s.first >= first && s.first + s.count <= first + count) s.head = 0;
+        if ((rc = clear_spatial_state(e, first, count)) != AW_OK) return rc;
+        AW_CUDA(cudaMemsetAsync(e->d_pending + (size_t)first * e->S * e->B, 0, (size_t)count * e->S * e->B * sizeof(float), e->stream));
+        AW_CUDA(cudaMemsetAsync(e->d_fifo + (size_t)first * 2 * e->fifoCap, 0, (size_t)count * 2 * e->fifoCap * sizeof(float), e->stream));
+        if (first == 0 && count == e->n) { e->pendingCount = 0; e->fifoReadIndex = 0; e->fifoCount = 0; }
+        AW_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    if (what & AW_RESET_EQ) {
+        split_machines(e, first);
+        split_machines(e, first + count);
+        for (EqMachine &m : e->machines)
+            if (m.first >= first && m.first + m.count <= first + count) m.resetRequested = true;   // :240-244
+    }
+    return AW_OK;
+}
+
+extern "C" int aw_engine_counters(const aw_engine *e, unsigned long long *kernel_launches, unsigned long long *blocks,
+                                  unsigned long long *h2d_bytes, unsigned long long *d2h_bytes)
+{
+    if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
+    if (kernel_launches) *kernel_launches = e->launches;
+    if (blocks) *blocks = e->blocks;
+    if (h2d_bytes) *h2d_bytes = e->h2dBytes;
+    if (d2h_bytes) *d2h_bytes = e->d2hBytes;
+    return AW_OK;
+}
+
+extern "C" void *aw_engine_stream(const aw_engine *e) { return e ? (void *)e->stream : nullptr; }
+
+extern "C" int aw_synth_fill_device(int device, float *d_out, int first_stream, int n_streams, int n_speakers, long long frame0,
+                                    int frames, uint32_t seed, void *cuda_stream)
+{
+    if (!d_out) return set_error(AW_ERR_INVALID_ARGUMENT, "null output");
+    DeviceGuard guard(device);
+    AW_CUDA(launch_synth_fill(d_out, first_stream, n_streams, n_speakers, frame0, frames, seed, (cudaStream_t)cuda_stream));
+    return AW_OK;
+}

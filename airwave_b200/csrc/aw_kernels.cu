@@ -1,0 +1,633 @@
+// aw_kernels.cu — hand-written sm_100a kernels of the batched binaural renderer.
+//
+//   K1 k_bank_build      ConvolutionEngine.init partition FFTs            (ConvolutionEngine.swift:143-182)
+//   K2 k_input_rfft      overlap-save frame + forward FFT + FDL write     (ConvolutionEngine.swift:237-264)
+//   K3 k_fdl_cmac        frequency-domain delay-line multiply-accumulate  (ConvolutionEngine.swift:270-350,
+//                        summed over speakers as RealtimeAudioProcessor.swift:146-163 does in time domain)
+//   K4 k_irfft_out       inverse FFT, scale, keep second half             (ConvolutionEngine.swift:353-366)
+//   K5 k_eq              float64 biquad cascade + 20 ms crossfade         (ParametricEqualizerProcessor.swift:58-91, 254-314)
+//   K6 k_resample_vgenp  Resampler.resampleHighQuality                    (Resampler.swift:31-68)
+//   K7 k_gather_pending / k_drain_fifo  frame adapter                     (RealtimeAudioProcessor.swift:88-116, 166-190)
+//
+// Layouts in HBM (B = block = bins per spectrum, P_cap = FDL slots per (stream, speaker)):
+//   FDL     float2 [stream][S][P_cap][B]      bin 0 = (2*DC, 0); Nyquist kept aside so the MAC is uniformly complex
+//   FDL_ny  float  [stream][S][P_cap]
+//   bank    float4 [S][P][B] = {L.re, L.im, R.re, R.im}; bank_ny float [S][P][2]
+//   acc     float2 [stream][2][B]
+#include "aw_kernels.h"
+
+#include <stdint.h>
+
+#include "aw_fft.cuh"
+
+namespace aw {
+
+using namespace awfft;
+
+static constexpr int kFftThreads = 256;
+
+int fft_batch(int log2m)
+{
+    int nf = (4 * kFftThreads) >> log2m;   // one radix-4 butterfly per thread per stage
+    if (nf < 1) nf = 1;
+    if (nf > 8) nf = 8;                    // <= one warp per transform for the Nyquist reduction in K4
+    return nf;
+}
+
+size_t fft_smem_bytes(int log2m)
+{
+    const size_t M = (size_t)1 << log2m;
+    return (M + 2 * (size_t)fft_batch(log2m) * M) * sizeof(float2) + 8 * sizeof(float);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  input_rfft
+// ------------------------------------------------------------------------------------------------
+struct InputRfftArgs {
+    BlockGeom g;
+    StridedIn cur, prev;
+    float *overlap_save;
+    float2 *fdl;
+    float *fdl_ny;
+    const float2 *tw;
+    int nf;
+};
+
+__global__ void __launch_bounds__(kFftThreads) k_input_rfft(const InputRfftArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int log2m = a.g.log2m, M = 1 << log2m, nf = a.nf, half = M >> 1;
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufA = tw + M;
+    float2 *bufB = bufA + (size_t)nf * M;
+    float *ny = reinterpret_cast<float *>(bufB + (size_t)nf * M);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int total_jobs = a.g.n_streams * a.g.S;
+    const int job0 = blockIdx.x * nf;
+
+    for (int k = tid; k < M; k += nth) tw[k] = a.tw[k];
+    // frame = [previous block | current block], packed as z[n] = x[2n] + i*x[2n+1]  (:237-248)
+    for (int idx = tid; idx < nf * M; idx += nth) {
+        const int f = idx >> log2m, n = idx & (M - 1);
+        const int job = job0 + f;
+        float2 v = make_float2(0.f, 0.f);
+        if (job < total_jobs) {
+            const int stream = a.g.first_stream + job / a.g.S, s = job % a.g.S;
+            if (n < half) v = *reinterpret_cast<const float2 *>(a.prev.ptr + stream * a.prev.ss + s * a.prev.cs + 2 * n);
+            else v = *reinterpret_cast<const float2 *>(a.cur.ptr + stream * a.cur.ss + s * a.cur.cs + 2 * (n - half));
+        }
+        bufA[idx] = v;
+    }
+    __syncthreads();
+    if (a.overlap_save != nullptr) {   // inputOverlapBuffer <- current block  (:243)
+        for (int idx = tid; idx < nf * half; idx += nth) {
+            const int f = idx / half, n = idx - f * half;
+            const int job = job0 + f;
+            if (job < total_jobs) {
+                const int stream = a.g.first_stream + job / a.g.S, s = job % a.g.S;
+                *reinterpret_cast<float2 *>(a.overlap_save + ((size_t)stream * a.g.Se + s) * a.g.B + 2 * n) = bufA[(size_t)f * M + half + n];
+            }
+        }
+    }
+    float2 *z = cfft_batched<false>(bufA, bufB, tw, log2m, nf);
+    float2 *spec = (z == bufA) ? bufB : bufA;
+    const int per = half + 1;
+    for (int i = tid; i < nf * per; i += nth) split_forward(z, spec, ny, tw, log2m, i);
+    __syncthreads();
+    // FDL[head] <- spectrum  (:256-264)
+    for (int idx = tid; idx < nf * M; idx += nth) {
+        const int f = idx >> log2m, k = idx & (M - 1);
+        const int job = job0 + f;
+        if (job < total_jobs) {
+            const int stream = a.g.first_stream + job / a.g.S, s = job % a.g.S;
+            const size_t row = ((size_t)stream * a.g.Se + s) * a.g.P_cap + a.g.head;
+            a.fdl[row * M + k] = spec[idx];
+            if (k == 0) a.fdl_ny[row] = ny[f];
+        }
+    }
+}
+
+cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl,
+                              float *fdl_ny, const float2 *tw, cudaStream_t st)
+{
+    InputRfftArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, tw, fft_batch(g.log2m)};
+    const int jobs = g.n_streams * g.S;
+    const int grid = (jobs + a.nf - 1) / a.nf;
+    if (grid <= 0) return cudaSuccess;
+    k_input_rfft<<<grid, kFftThreads, fft_smem_bytes(g.log2m), st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  fdl_cmac — the bandwidth-bound core.  One thread owns two adjacent bins of T streams: the
+// filter values are loaded once into registers and reused for the T streams of the tile; the FDL
+// is read exactly once (float4 = 2 complex bins, fully coalesced); partial sums over partitions AND
+// speakers stay in registers, nothing intermediate is written.
+// ------------------------------------------------------------------------------------------------
+static constexpr int kMacThreads = 128;
+
+__device__ __forceinline__ float4 ldg_stream(const float4 *p)
+{
+    float4 r;   // FDL history is read once per block: do not allocate in L1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void cmac2(float4 &acc, const float4 x, const float hr0, const float hi0, const float hr1, const float hi1)
+{
+    acc.x = fmaf(x.x, hr0, acc.x); acc.x = fmaf(-x.y, hi0, acc.x);
+    acc.y = fmaf(x.x, hi0, acc.y); acc.y = fmaf(x.y, hr0, acc.y);
+    acc.z = fmaf(x.z, hr1, acc.z); acc.z = fmaf(-x.w, hi1, acc.z);
+    acc.w = fmaf(x.z, hi1, acc.w); acc.w = fmaf(x.w, hr1, acc.w);
+}
+
+template <int T>
+__global__ void __launch_bounds__(kMacThreads) k_fdl_cmac(const BlockGeom g, const float4 *__restrict__ fdl,
+                                                           const float4 *__restrict__ bank, float4 *__restrict__ acc)
+{
+    const int halfB = g.B >> 1;
+    const int chunks = (halfB + kMacThreads - 1) / kMacThreads;
+    const int tile = blockIdx.x / chunks, chunk = blockIdx.x - tile * chunks;
+    const int jp = chunk * kMacThreads + threadIdx.x;
+    if (jp >= halfB) return;
+    const int s0 = g.first_stream + tile * T;
+    const int last = g.first_stream + g.n_streams - 1;
+    const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+    const float4 *fp[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) fp[t] = fdl + (size_t)min(s0 + t, last) * stream_stride + jp;
+    float4 aL[T], aR[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) { aL[t] = make_float4(0.f, 0.f, 0.f, 0.f); aR[t] = aL[t]; }
+
+    for (int s = 0; s < g.S; ++s) {
+        const float4 *bk = bank + (size_t)s * g.P * g.B + 2 * jp;
+        const size_t srow = (size_t)s * g.P_cap;
+        int slot = g.head;
+#pragma unroll 2
+        for (int p = 0; p < g.P; ++p) {
+            const float4 h0 = __ldg(bk + (size_t)p * g.B);
+            const float4 h1 = __ldg(bk + (size_t)p * g.B + 1);
+            const size_t off = (srow + slot) * halfB;
+            float4 x[T];
+#pragma unroll
+            for (int t = 0; t < T; ++t) x[t] = ldg_stream(fp[t] + off);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                cmac2(aL[t], x[t], h0.x, h0.y, h1.x, h1.y);
+                cmac2(aR[t], x[t], h0.z, h0.w, h1.z, h1.w);
+            }
+            slot = (slot + 1 == g.P) ? 0 : slot + 1;   // modulus is partitionCount, not a power of two (Q4)
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        if (s0 + t <= last) {
+            acc[((size_t)(s0 + t) * 2 + 0) * halfB + jp] = aL[t];
+            acc[((size_t)(s0 + t) * 2 + 1) * halfB + jp] = aR[t];
+        }
+    }
+}
+
+cudaError_t launch_fdl_cmac(const BlockGeom &g, const float2 *fdl, const float4 *bank, float2 *acc, int tile, cudaStream_t st)
+{
+    const int halfB = g.B >> 1;
+    const int chunks = (halfB + kMacThreads - 1) / kMacThreads;
+    const int tiles = (g.n_streams + tile - 1) / tile;
+    const int grid = tiles * chunks;
+    if (grid <= 0) return cudaSuccess;
+    const float4 *f4 = reinterpret_cast<const float4 *>(fdl);
+    float4 *a4 = reinterpret_cast<float4 *>(acc);
+    switch (tile) {
+    case 1: k_fdl_cmac<1><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
+    case 2: k_fdl_cmac<2><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
+    case 4: k_fdl_cmac<4><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
+    case 8: k_fdl_cmac<8><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  irfft_out
+// ------------------------------------------------------------------------------------------------
+struct IrfftArgs {
+    BlockGeom g;
+    const float2 *acc;
+    const float *fdl_ny;
+    const float *bank_ny;
+    StridedOut out;
+    const float2 *tw;
+    int nf;
+};
+
+__global__ void __launch_bounds__(kFftThreads) k_irfft_out(const IrfftArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int log2m = a.g.log2m, M = 1 << log2m, nf = a.nf, half = M >> 1;
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufA = tw + M;
+    float2 *bufB = bufA + (size_t)nf * M;
+    float *ny = reinterpret_cast<float *>(bufB + (size_t)nf * M);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int total_jobs = a.g.n_streams * 2;   // (stream, ear)
+    const int job0 = blockIdx.x * nf;
+
+    for (int k = tid; k < M; k += nth) tw[k] = a.tw[k];
+    for (int idx = tid; idx < nf * M; idx += nth) {
+        const int f = idx >> log2m, k = idx & (M - 1);
+        const int job = job0 + f;
+        float2 v = make_float2(0.f, 0.f);
+        if (job < total_jobs) v = a.acc[((size_t)a.g.first_stream * 2 + job) * M + k];
+        bufA[idx] = v;
+    }
+    // Nyquist bin: imagp[0] products of ConvolutionEngine.swift:305,337, summed over partitions and speakers
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < nf) {
+            const int job = job0 + warp;
+            float sum = 0.f;
+            if (job < total_jobs) {
+                const int stream = a.g.first_stream + (job >> 1), ear = job & 1;
+                const int terms = a.g.S * a.g.P;
+                for (int i = lane; i < terms; i += 32) {
+                    const int s = i / a.g.P, p = i - s * a.g.P;
+                    int slot = a.g.head + p;
+                    if (slot >= a.g.P) slot -= a.g.P;
+                    sum = fmaf(a.fdl_ny[((size_t)stream * a.g.Se + s) * a.g.P_cap + slot], a.bank_ny[(size_t)i * 2 + ear], sum);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) ny[warp] = sum;
+        }
+    }
+    __syncthreads();
+    const int per = half + 1;
+    for (int i = tid; i < nf * per; i += nth) split_inverse(bufA, ny, bufB, tw, log2m, i);
+    __syncthreads();
+    float2 *z = cfft_batched<true>(bufB, bufA, tw, log2m, nf);
+    // valid output = second half of the frame (:366): x[B + i], i < B  <=>  z[M/2 + i/2].{x,y}
+    const int B = a.g.B;
+    for (int idx = tid; idx < nf * B; idx += nth) {
+        const int f = idx / B, i = idx - f * B;
+        const int job = job0 + f;
+        if (job < total_jobs) {
+            const int stream = a.g.first_stream + (job >> 1), ear = job & 1;
+            const float2 v = z[(size_t)f * M + half + (i >> 1)];
+            int pos = i;
+            if (a.out.ring_cap > 0) { pos = a.out.ring_start + i; if (pos >= a.out.ring_cap) pos -= a.out.ring_cap; }
+            a.out.ptr[stream * a.out.ss + ear * a.out.cs + pos] = (i & 1) ? v.y : v.x;
+        }
+    }
+}
+
+cudaError_t launch_irfft_out(const BlockGeom &g, const float2 *acc, const float *fdl_ny, const float *bank_ny,
+                             StridedOut out, const float2 *tw, cudaStream_t st)
+{
+    IrfftArgs a{g, acc, fdl_ny, bank_ny, out, tw, fft_batch(g.log2m)};
+    const int jobs = g.n_streams * 2;
+    const int grid = (jobs + a.nf - 1) / a.nf;
+    if (grid <= 0) return cudaSuccess;
+    k_irfft_out<<<grid, kFftThreads, fft_smem_bytes(g.log2m), st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  bank_build: h[pB .. (p+1)B) || 0_B  ->  rfft  ->  x 0.25/N  (exact power-of-two scaling)
+// ------------------------------------------------------------------------------------------------
+struct BankArgs {
+    const float *ir;   // [S][2][taps]
+    int S, taps, B, log2m, P, nf;
+    float4 *bank;
+    float *bank_ny;
+    const float2 *tw;
+};
+
+__global__ void __launch_bounds__(kFftThreads) k_bank_build(const BankArgs a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int log2m = a.log2m, M = 1 << log2m, nf = a.nf, half = M >> 1;
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufA = tw + M;
+    float2 *bufB = bufA + (size_t)nf * M;
+    float *ny = reinterpret_cast<float *>(bufB + (size_t)nf * M);
+    const int tid = threadIdx.x, nth = blockDim.x;
+    const int total_jobs = a.S * 2 * a.P;   // job = (s*2 + ear)*P + p
+    const int job0 = blockIdx.x * nf;
+    for (int k = tid; k < M; k += nth) tw[k] = a.tw[k];
+    for (int idx = tid; idx < nf * M; idx += nth) {
+        const int f = idx >> log2m, n = idx & (M - 1);
+        const int job = job0 + f;
+        float2 v = make_float2(0.f, 0.f);
+        if (job < total_jobs && n < half) {
+            const int se = job / a.P, p = job - se * a.P;
+            const int t0 = p * a.B + 2 * n;
+            const float *h = a.ir + (size_t)se * a.taps;
+            if (t0 < a.taps) v.x = h[t0];
+            if (t0 + 1 < a.taps) v.y = h[t0 + 1];
+        }
+        bufA[idx] = v;
+    }
+    __syncthreads();
+    float2 *z = cfft_batched<false>(bufA, bufB, tw, log2m, nf);
+    float2 *spec = (z == bufA) ? bufB : bufA;
+    for (int i = tid; i < nf * (half + 1); i += nth) split_forward(z, spec, ny, tw, log2m, i);
+    __syncthreads();
+    const float scale = 0.25f / (float)(2 * a.B);   // ConvolutionEngine.swift:356, folded into the bank
+    for (int idx = tid; idx < nf * M; idx += nth) {
+        const int f = idx >> log2m, k = idx & (M - 1);
+        const int job = job0 + f;
+        if (job < total_jobs) {
+            const int se = job / a.P, p = job - se * a.P;
+            const int s = se >> 1, ear = se & 1;
+            float *dst = reinterpret_cast<float *>(a.bank + ((size_t)s * a.P + p) * a.B + k) + 2 * ear;
+            dst[0] = spec[idx].x * scale;
+            dst[1] = spec[idx].y * scale;
+            if (k == 0) a.bank_ny[((size_t)s * a.P + p) * 2 + ear] = ny[f] * scale;
+        }
+    }
+}
+
+cudaError_t launch_bank_build(const float *ir, int S, int taps, int B, int log2m, int P, float4 *bank, float *bank_ny,
+                              const float2 *tw, cudaStream_t st)
+{
+    BankArgs a{ir, S, taps, B, log2m, P, fft_batch(log2m), bank, bank_ny, tw};
+    const int jobs = S * 2 * P;
+    const int grid = (jobs + a.nf - 1) / a.nf;
+    k_bank_build<<<grid, kFftThreads, fft_smem_bytes(log2m), st>>>(a);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6  resample (vDSP_vramp + vDSP_vgenp semantics).  Bit-exact with the oracle:
+// explicit round-to-nearest mul/add so nvcc cannot contract them into FMAs.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_resample_vgenp(const float *__restrict__ in, int rows, int count, float step, float *__restrict__ out, int out_count)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (n >= out_count || row >= rows) return;
+    const float *x = in + (size_t)row * count;
+    const int M = count;
+    const float fn = (float)n;
+    const float bLast = __fmul_rn((float)(M - 1), step);
+    float r;
+    if (fn <= 0.0f) r = x[0];                       // n <= trunc(B[0]) = 0
+    else if (fn > truncf(bLast)) r = x[M - 1];      // beyond the last breakpoint: hold
+    else {
+        int m = (int)(fn / step);
+        if (m > M - 2) m = M - 2;
+        if (m < 0) m = 0;
+        while (m + 1 < M && truncf(__fmul_rn((float)(m + 1), step)) < fn) ++m;   // largest m with trunc(B[m]) < n
+        while (m > 0 && !(truncf(__fmul_rn((float)m, step)) < fn)) --m;
+        const float bm = __fmul_rn((float)m, step), bm1 = __fmul_rn((float)(m + 1), step);
+        // reference order: A[m] + (A[m+1]-A[m]) * (n - B[m]) / (B[m+1]-B[m]); the oracle evaluates (d*(n-bm))/(bm1-bm)
+        const float d = __fsub_rn(x[m + 1], x[m]);
+        r = __fadd_rn(x[m], __fdiv_rn(__fmul_rn(d, __fsub_rn(fn, bm)), __fsub_rn(bm1, bm)));
+    }
+    out[(size_t)row * out_count + n] = r;
+}
+
+cudaError_t launch_resample_vgenp(const float *in, int rows, int count, float step, float *out, int out_count, cudaStream_t st)
+{
+    if (rows <= 0 || out_count <= 0) return cudaSuccess;
+    dim3 grid((out_count + 255) / 256, rows);
+    k_resample_vgenp<<<grid, 256, 0, st>>>(in, rows, count, step, out, out_count);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7  frame adapter
+// ------------------------------------------------------------------------------------------------
+__global__ void k_gather_pending(StridedIn in, int in_offset, int copy_count, float *pending, int pending_count, int n_streams,
+                                 int S, int B, int dup_mono)
+{
+    const long long total = (long long)n_streams * S * copy_count;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % copy_count);
+        const long long row = idx / copy_count;
+        const int s = (int)(row % S);
+        const long long stream = row / S;
+        const int src_ch = (dup_mono && s == 1) ? 0 : s;   // nil right input: duplicate left (:101-107)
+        pending[(stream * S + s) * B + pending_count + i] = in.ptr[stream * in.ss + src_ch * in.cs + in_offset + i];
+    }
+}
+
+cudaError_t launch_gather_pending(StridedIn in, int in_offset, int copy_count, float *pending, int pending_count, int n_streams,
+                                  int S, int B, int dup_mono, cudaStream_t st)
+{
+    const long long total = (long long)n_streams * S * copy_count;
+    if (total <= 0) return cudaSuccess;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_gather_pending<<<grid, 256, 0, st>>>(in, in_offset, copy_count, pending, pending_count, n_streams, S, B, dup_mono);
+    return cudaGetLastError();
+}
+
+__global__ void k_drain_fifo(const float *__restrict__ fifo, int fifo_cap, int fifo_read, int fifo_count, StridedOut out,
+                             int out_offset, int frames, int n_streams)
+{
+    const long long total = (long long)n_streams * 2 * frames;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % frames);
+        const long long row = idx / frames;     // stream*2 + ear
+        float v = 0.f;                          // underflow: silence (:185-188)
+        if (i < fifo_count) {
+            int pos = fifo_read + i;
+            if (pos >= fifo_cap) pos -= fifo_cap;
+            v = fifo[row * fifo_cap + pos];
+        }
+        out.ptr[(row >> 1) * out.ss + (row & 1) * out.cs + out_offset + i] = v;
+    }
+}
+
+cudaError_t launch_drain_fifo(const float *fifo, int fifo_cap, int fifo_read, int fifo_count, StridedOut out, int out_offset,
+                              int frames, int n_streams, cudaStream_t st)
+{
+    const long long total = (long long)n_streams * 2 * frames;
+    if (total <= 0) return cudaSuccess;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_drain_fifo<<<grid, 256, 0, st>>>(fifo, fifo_cap, fifo_read, fifo_count, out, out_offset, frames, n_streams);
+    return cudaGetLastError();
+}
+
+__global__ void k_passthrough(StridedIn in, StridedOut out, int first_stream, int n_streams, int S, int frames)
+{
+    const long long total = (long long)n_streams * 2 * frames;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % frames);
+        const long long row = idx / frames;
+        const long long stream = first_stream + (row >> 1);
+        const int ear = (int)(row & 1);
+        const int ch = (ear == 1 && S > 1) ? 1 : 0;
+        out.ptr[stream * out.ss + ear * out.cs + i] = in.ptr[stream * in.ss + ch * in.cs + i];
+    }
+}
+
+cudaError_t launch_passthrough(StridedIn in, StridedOut out, int first_stream, int n_streams, int S, int frames, cudaStream_t st)
+{
+    const long long total = (long long)n_streams * 2 * frames;
+    if (total <= 0) return cudaSuccess;
+    const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+    k_passthrough<<<grid, 256, 0, st>>>(in, out, first_stream, n_streams, S, frames);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// Synthetic input: counter-based hash keyed by (seed, stream, speaker, frame), SURVEY.md 8(d)
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+    return x;
+}
+
+__global__ void k_synth_fill(float *out, int first_stream, int n_streams, int S, long long frame0, int frames, uint32_t seed)
+{
+    const long long total = (long long)n_streams * S * frames;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % frames);
+        const long long row = idx / frames;
+        const uint32_t s = (uint32_t)(row % S), stream = (uint32_t)(first_stream + row / S);
+        uint32_t h = mix32(seed ^ mix32(stream * 0x9E3779B9U + 0x85EBCA6BU));
+        h = mix32(h ^ (s * 0xC2B2AE35U + 0x27D4EB2FU));
+        h = mix32(h ^ ((uint32_t)(frame0 + i) * 0x165667B1U + 0x9E3779B9U));
+        out[idx] = ((float)(h >> 8) * (1.0f / 16777216.0f) - 0.5f) * 0.5f;
+    }
+}
+
+cudaError_t launch_synth_fill(float *out, int first_stream, int n_streams, int S, long long frame0, int frames, uint32_t seed,
+                              cudaStream_t st)
+{
+    const long long total = (long long)n_streams * S * frames;
+    if (total <= 0) return cudaSuccess;
+    const int grid = (int)((total + 255) / 256 < 148 * 32 ? (total + 255) / 256 : 148 * 32);
+    k_synth_fill<<<grid, 256, 0, st>>>(out, first_stream, n_streams, S, frame0, frames, seed);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5  eq: one thread per (stream, ear) channel; filter state in registers (FMAX bucket), float64.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double flush_subnormal(double v) { return fabs(v) < 1e-30 ? 0.0 : v; }   // :94-97
+
+template <int FMAX>
+__device__ __forceinline__ double biquad_cascade(double x, const EqProgram *__restrict__ prog, int nf, double (&z1)[FMAX], double (&z2)[FMAX])
+{
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) {
+        if (f < nf) {
+            const double b0 = prog->coef[f][0], b1 = prog->coef[f][1], b2 = prog->coef[f][2], a1 = prog->coef[f][3], a2 = prog->coef[f][4];
+            // no FMA contraction: the reference (and the oracle) round every product and sum (:73-75)
+            const double y = __dadd_rn(__dmul_rn(b0, x), z1[f]);
+            const double n1 = __dadd_rn(__dsub_rn(__dmul_rn(b1, x), __dmul_rn(a1, y)), z2[f]);
+            const double n2 = __dsub_rn(__dmul_rn(b2, x), __dmul_rn(a2, y));
+            z1[f] = flush_subnormal(n1);
+            z2[f] = flush_subnormal(n2);
+            x = y;
+        }
+    }
+    return x;
+}
+
+template <int FMAX>
+__global__ void __launch_bounds__(64) k_eq(const EqLaunch l, double *__restrict__ zstate, StridedOut io)
+{
+    __shared__ EqProgram progs[2];
+    {
+        const int words = (int)(sizeof(EqProgram) / sizeof(double));
+        const double *src0 = reinterpret_cast<const double *>(l.from);
+        double *dst0 = reinterpret_cast<double *>(&progs[0]);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst0[i] = src0[i];
+        if (l.to != nullptr) {
+            const double *src1 = reinterpret_cast<const double *>(l.to);
+            double *dst1 = reinterpret_cast<double *>(&progs[1]);
+            for (int i = threadIdx.x; i < words; i += blockDim.x) dst1[i] = src1[i];
+        }
+    }
+    __syncthreads();
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;   // channel = stream*2 + ear within the launch
+    if (ch >= l.n_streams * 2) return;
+    const int stream = l.first_stream + (ch >> 1), ear = ch & 1;
+    const bool fading = l.to != nullptr;
+    const int nfA = progs[0].n_filters, nfB = fading ? progs[1].n_filters : 0;
+    double zA1[FMAX], zA2[FMAX], zB1[FMAX], zB2[FMAX];
+    double *zA = zstate + ((((size_t)stream * 2 + l.from_voice) * 2 + ear) * 64) * 2;
+    double *zB = zstate + ((((size_t)stream * 2 + l.to_voice) * 2 + ear) * 64) * 2;
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) {
+        zA1[f] = f < nfA ? zA[2 * f] : 0.0; zA2[f] = f < nfA ? zA[2 * f + 1] : 0.0;
+        zB1[f] = (fading && f < nfB) ? zB[2 * f] : 0.0; zB2[f] = (fading && f < nfB) ? zB[2 * f + 1] : 0.0;
+    }
+    float *p = io.ptr + stream * io.ss + ear * io.cs + l.seg_start;
+    const double preA = progs[0].preamp_linear, preB = fading ? progs[1].preamp_linear : 1.0;
+    for (int i = 0; i < l.seg_len; ++i) {
+        const double x = (double)p[i];
+        const float yo = (float)biquad_cascade<FMAX>(__dmul_rn(x, preA), &progs[0], nfA, zA1, zA2);   // :66, :88
+        float r = yo;
+        if (fading) {
+            const float yn = (float)biquad_cascade<FMAX>(__dmul_rn(x, preB), &progs[1], nfB, zB1, zB2);
+            const double progress = (double)(l.transition_frame + i + 1) / (double)l.transition_length;   // :298
+            const double inverse = 1.0 - progress;
+            r = (float)__dadd_rn(__dmul_rn((double)yo, inverse), __dmul_rn((double)yn, progress));        // :300-302
+        }
+        p[i] = r;
+    }
+#pragma unroll
+    for (int f = 0; f < FMAX; ++f) {
+        if (f < nfA) { zA[2 * f] = zA1[f]; zA[2 * f + 1] = zA2[f]; }
+        if (fading && f < nfB) { zB[2 * f] = zB1[f]; zB[2 * f + 1] = zB2[f]; }
+    }
+}
+
+template <int FMAX>
+static cudaError_t launch_eq_t(const EqLaunch &l, double *z, StridedOut io, cudaStream_t st)
+{
+    const int channels = l.n_streams * 2;
+    const int grid = (channels + 63) / 64;
+    k_eq<FMAX><<<grid, 64, 0, st>>>(l, z, io);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eq(const EqLaunch &l, int max_filters, double *z, StridedOut io, cudaStream_t st)
+{
+    if (l.n_streams <= 0 || l.seg_len <= 0) return cudaSuccess;
+    if (max_filters <= 4) return launch_eq_t<4>(l, z, io, st);
+    if (max_filters <= 8) return launch_eq_t<8>(l, z, io, st);
+    if (max_filters <= 16) return launch_eq_t<16>(l, z, io, st);
+    if (max_filters <= 32) return launch_eq_t<32>(l, z, io, st);
+    return launch_eq_t<64>(l, z, io, st);
+}
+
+__global__ void k_eq_reset(double *z, int first_stream, int n_streams, int voice_mask)
+{
+    const long long per_voice = 2 * 64 * 2;
+    const long long total = (long long)n_streams * 2 * per_voice;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+        const long long sv = idx / per_voice;   // stream*2 + voice
+        const int voice = (int)(sv & 1);
+        if ((voice_mask >> voice) & 1) z[(long long)first_stream * 2 * per_voice + idx] = 0.0;
+    }
+}
+
+cudaError_t launch_eq_reset(double *z, int first_stream, int n_streams, int voice_mask, cudaStream_t st)
+{
+    if (n_streams <= 0) return cudaSuccess;
+    const long long total = (long long)n_streams * 2 * 2 * 64 * 2;
+    const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+    k_eq_reset<<<grid, 256, 0, st>>>(z, first_stream, n_streams, voice_mask);
+    return cudaGetLastError();
+}
+
+cudaError_t configure_kernels(int max_log2m)
+{
+    const int bytes = (int)fft_smem_bytes(max_log2m);
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_input_rfft, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_irfft_out, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_bank_build, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+}  // namespace aw

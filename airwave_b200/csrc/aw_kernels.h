@@ -1,0 +1,80 @@
+// aw_kernels.h — host-callable launchers of the sm_100a kernels (internal to libairwave_cuda.so).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace aw {
+
+// Geometry shared by the per-block kernels of one engine segment (streams that share a bank).
+struct BlockGeom {
+    int first_stream;   // first stream of the segment
+    int n_streams;      // streams in the segment
+    int S;              // renderers of the segment's bank (speakers convolved)
+    int Se;             // speakers per stream the engine's state arrays are laid out for (S <= Se)
+    int B;              // block size = complex bins per spectrum
+    int log2m;          // log2(B)
+    int P;              // partitions of the segment's bank (ring modulus, ConvolutionEngine.swift:256-259)
+    int P_cap;          // FDL slots allocated per (stream, speaker)
+    int head;           // fdlIndex after the decrement for this block
+};
+
+struct StridedIn {      // planar input: ptr[stream*ss + channel*cs + i]
+    const float *ptr;
+    long long ss, cs;
+};
+
+struct StridedOut {     // planar output; when ring_cap > 0 sample i lands at (ring_start + i) % ring_cap
+    float *ptr;
+    long long ss, cs;
+    int ring_cap, ring_start;
+};
+
+// K2: [prev | cur] -> real FFT -> FDL slot `head` (+ Nyquist side array); optionally saves cur as next overlap.
+cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl,
+                              float *fdl_ny, const float2 *tw, cudaStream_t st);
+// K3: acc[stream][ear][bin] = sum_{s,p} FDL[stream][s][(head+p)%P][bin] * bank[s][p][bin].ear
+cudaError_t launch_fdl_cmac(const BlockGeom &g, const float2 *fdl, const float4 *bank, float2 *acc, int tile, cudaStream_t st);
+// K4: Nyquist reduction + inverse real FFT + overlap-save discard -> out (planar or FIFO ring)
+cudaError_t launch_irfft_out(const BlockGeom &g, const float2 *acc, const float *fdl_ny, const float *bank_ny,
+                             StridedOut out, const float2 *tw, cudaStream_t st);
+// K1: partition + zero-pad + real FFT of every (speaker, ear) impulse response -> filter bank
+cudaError_t launch_bank_build(const float *ir, int S, int taps, int B, int log2m, int P, float4 *bank, float *bank_ny,
+                              const float2 *tw, cudaStream_t st);
+// K6: Resampler.resampleHighQuality (vDSP_vramp + vDSP_vgenp semantics), rows x count -> rows x out_count
+cudaError_t launch_resample_vgenp(const float *in, int rows, int count, float step, float *out, int out_count, cudaStream_t st);
+// K7: frame adapter pieces (RealtimeAudioProcessor.swift:88-116, 166-171, 174-190)
+cudaError_t launch_gather_pending(StridedIn in, int in_offset, int copy_count, float *pending, int pending_count, int n_streams,
+                                  int S, int B, int dup_mono, cudaStream_t st);
+cudaError_t launch_drain_fifo(const float *fifo, int fifo_cap, int fifo_read, int fifo_count, StridedOut out, int out_offset,
+                              int frames, int n_streams, cudaStream_t st);
+// passthrough (HRIRManager.swift:555-564): L = channel 0, R = channel 1 (or channel 0 when mono)
+cudaError_t launch_passthrough(StridedIn in, StridedOut out, int first_stream, int n_streams, int S, int frames, cudaStream_t st);
+cudaError_t launch_synth_fill(float *out, int first_stream, int n_streams, int S, long long frame0, int frames, uint32_t seed,
+                              cudaStream_t st);
+
+// K5: stereo float64 TDF-II biquad cascade (ParametricEqualizerState.process, ParametricEqualizerProcessor.swift:58-91)
+// with the 20 ms crossfade of ParametricEqualizerProcessor.process (:254-314).
+struct EqProgram {          // one ParametricEqualizerState's immutable part, resident in HBM
+    double preamp_linear;
+    int n_filters;
+    int pad;
+    double coef[64][5];     // b0 b1 b2 a1 a2
+};
+struct EqLaunch {
+    int first_stream, n_streams;
+    const EqProgram *from;  // program producing the "old" signal (the active state when no transition)
+    const EqProgram *to;    // transition target or nullptr
+    int from_voice, to_voice;   // which z-state voice each program uses
+    int seg_start, seg_len; // frames [seg_start, seg_start+seg_len) of this call
+    int transition_frame;   // transitionFrame at seg_start (only when to != nullptr)
+    int transition_length;
+};
+// z: [stream][voice(2)][ear(2)][filter(64)][2] doubles; io: planar stereo in place.
+cudaError_t launch_eq(const EqLaunch &l, int max_filters, double *z, StridedOut io, cudaStream_t st);
+cudaError_t launch_eq_reset(double *z, int first_stream, int n_streams, int voice_mask, cudaStream_t st);
+
+int fft_batch(int log2m);                 // transforms per CTA used by K1/K2/K4
+size_t fft_smem_bytes(int log2m);
+cudaError_t configure_kernels(int max_log2m);   // opt in to > 48 KB dynamic shared memory
+
+}  // namespace aw
