@@ -147,6 +147,10 @@ struct aw_engine {
     // adapter counters (RealtimeAudioProcessor.swift:26-28)
     int pendingCount = 0, fifoReadIndex = 0, fifoCount = 0;
     unsigned long long launches = 0, blocks = 0, h2dBytes = 0, d2hBytes = 0;
+    // optional per-kernel event timing (benchmarks only)
+    std::vector<cudaEvent_t> profEvents;
+    size_t profUsed = 0;
+    bool profOn = false;
 };
 
 namespace {
@@ -403,9 +407,15 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         g.P = b->P;
         g.P_cap = e->P_cap;
         g.head = seg.head;
+        const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
+        cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
+        if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
         AW_LAUNCH(e, launch_input_rfft(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, e->d_tw, e->stream));
+        if (prof) cudaEventRecord(ev[1], e->stream);
         AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, b->d_bank, e->d_acc, e->macTile, e->stream));
+        if (prof) cudaEventRecord(ev[2], e->stream);
         AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, b->d_ny, out, e->d_tw, e->stream));
+        if (prof) cudaEventRecord(ev[3], e->stream);
     }
     ++e->blocks;
     return AW_OK;
@@ -493,6 +503,7 @@ void free_engine(aw_engine *e)
         if (s.compute_done) cudaEventDestroy(s.compute_done);
         if (s.out_done) cudaEventDestroy(s.out_done);
     }
+    for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
     if (e->d2h) cudaStreamDestroy(e->d2h);
@@ -1090,6 +1101,45 @@ extern "C" int aw_engine_counters(const aw_engine *e, unsigned long long *kernel
     if (blocks) *blocks = e->blocks;
     if (h2d_bytes) *h2d_bytes = e->h2dBytes;
     if (d2h_bytes) *d2h_bytes = e->d2hBytes;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_profile_begin(aw_engine *e, int max_blocks)
+{
+    if (!e || max_blocks <= 0) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_profile_begin: bad argument");
+    DeviceGuard guard(e->cfg.device);
+    const size_t want = (size_t)max_blocks * 4 * std::max<size_t>(1, e->segments.size());
+    while (e->profEvents.size() < want) {
+        cudaEvent_t ev;
+        AW_CUDA(cudaEventCreate(&ev));
+        e->profEvents.push_back(ev);
+    }
+    e->profUsed = 0;
+    e->profOn = true;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_profile_end(aw_engine *e, double *kernel_ms, unsigned long long *kernel_launches)
+{
+    if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
+    DeviceGuard guard(e->cfg.device);
+    e->profOn = false;
+    AW_CUDA(cudaStreamSynchronize(e->stream));
+    double ms[3] = {0, 0, 0};
+    unsigned long long cnt[3] = {0, 0, 0};
+    for (size_t i = 0; i + 4 <= e->profUsed; i += 4) {
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.f;
+            AW_CUDA(cudaEventElapsedTime(&t, e->profEvents[i + k], e->profEvents[i + k + 1]));
+            ms[k] += t;
+            ++cnt[k];
+        }
+    }
+    for (int k = 0; k < 3; ++k) {
+        if (kernel_ms) kernel_ms[k] = ms[k];
+        if (kernel_launches) kernel_launches[k] = cnt[k];
+    }
+    e->profUsed = 0;
     return AW_OK;
 }
 

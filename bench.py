@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py — binaural stream-seconds rendered per second (7.1 -> 2 ch, 48 kHz) on N B200s.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host cores
+
+A step = one block of B frames rendered for every stream of the workload (one pass of the hot
+path: K2 input_rfft -> K3 fdl_cmac -> K4 irfft_out).  The default workload is BASELINE.json
+configs[1] ("C2"): 7.1 (8 virtual speakers) -> binaural, RoomSH1.0 HeSuVi 14-ch HRIR, 256-frame
+blocks, 4,096 concurrent streams per GPU (weak scaling: streams are independent, no collective).
+
+`value`  : whole-job stream-s/s with inputs resident in HBM (device events, max over ranks).
+`e2e`    : same metric through aw_engine_submit/aw_engine_wait with pinned HOST buffers, every
+           step's input copied H2D and its output copied D2H inside the timed region.
+`roofline`: the dominant kernel (K3 fdl_cmac): algorithmic bytes per launch / its mean duration
+           (CUDA events around each launch on the engine's stream) vs MEASURED_PEAKS.json.
+`cpu_baseline`: the oracle (C restatement of the reference algorithm) on the host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 48000.0
+SEED = 0x41495257
+METRIC = "binaural stream-sec/sec (7.1->2ch, 48 kHz)"
+UNIT = "stream-s/s"
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+WORKLOADS = {
+    # name: (description, speakers, block, streams per GPU, hrir)
+    "C2": ("7.1->binaural, RoomSH1.0 HeSuVi 14-ch HRIR (4320 taps), B=256, 4096 streams/GPU", 8, 256, 4096, "RoomSH1.0"),
+    "C1": ("stereo->binaural, NeutralSH1.0, B=512, single stream", 2, 512, 1, "NeutralSH1.0"),
+    "C3": ("7.1->binaural, synthetic 65,536-tap BRIR, B=512, 1024 streams/GPU", 8, 512, 1024, "synthetic65536"),
+    "C5-64": ("7.1->binaural, RoomSH1.0, B=64, 2048 streams/GPU", 8, 64, 2048, "RoomSH1.0"),
+    "C5-128": ("7.1->binaural, RoomSH1.0, B=128, 2048 streams/GPU", 8, 128, 2048, "RoomSH1.0"),
+    "C5-512": ("7.1->binaural, RoomSH1.0, B=512, 2048 streams/GPU", 8, 512, 2048, "RoomSH1.0"),
+    "C5-1024": ("7.1->binaural, RoomSH1.0, B=1024, 2048 streams/GPU", 8, 1024, 2048, "RoomSH1.0"),
+    "C5-2048": ("7.1->binaural, RoomSH1.0, B=2048, 2048 streams/GPU", 8, 2048, 2048, "RoomSH1.0"),
+    "C5-4096": ("7.1->binaural, RoomSH1.0, B=4096, 2048 streams/GPU", 8, 4096, 2048, "RoomSH1.0"),
+}
+
+
+def hrir_pcm(name: str):
+    """Returns (pcm [channels][frames] float32, sample_rate)."""
+    import numpy as np
+    if name == "synthetic65536":   # 0.5*delta[n-190] + 0.05*N(0,1)*exp(-n/(0.25 fs)), seed 1
+        rng = np.random.default_rng(1)
+        n = np.arange(65536)
+        pcm = (0.05 * rng.standard_normal((14, 65536)) * np.exp(-n / (0.25 * FS))).astype(np.float32)
+        pcm[:, 190] += 0.5
+        return pcm, FS
+    import airwave_b200 as aw
+    wav = aw.WAVLoader.load(os.path.join(GOLDEN, "hrtf", name + ".wav"))
+    return wav.audioData, wav.sampleRate
+
+
+def speaker_maps(S: int):
+    import airwave_b200 as aw
+    lay = aw.InputLayout.detect(S)
+    m = aw.HRIRChannelMap.hesuvi14Channel(lay.channels)
+    return [m.getIndices(s)[0] for s in lay.channels], [m.getIndices(s)[1] for s in lay.channels]
+
+
+def algorithmic_bytes(S: int, B: int, P: int) -> int:
+    """per stream per block, FDL ring (1 slot written + P-1 read) + input + output."""
+    return 8 * S * B * P + 4 * S * B + 8 * B
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.file, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.file.flush()
+        rows = [r.strip().split(",") for r in open(self.file.name).read().splitlines() if r.strip()]
+        os.unlink(self.file.name)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_sample(S, B, pcm, l_idx, r_idx, budget_s, threads=0):
+    """Times the oracle (C restatement of the reference) on a bounded sample of the workload."""
+    import numpy as np
+    import oracle
+    taps = pcm.shape[1]
+    h = np.zeros((S, 2, taps), np.float32)
+    for s in range(S):
+        h[s, 0], h[s, 1] = pcm[l_idx[s]], pcm[r_idx[s]]
+    cores = oracle.max_threads() if threads <= 0 else threads
+    streams = max(cores * 4, 8)
+    batch = oracle.CpuBatch(streams, S, B, h)
+    sec, _ = batch.step(2, cores)                          # pilot (also warms the FDL)
+    per_block = max(sec / 2, 1e-6)
+    blocks = int(max(4, min(4000, budget_s / per_block)))
+    sec, _ = batch.step(blocks, cores)
+    value = streams * blocks * (B / FS) / sec
+    return value, cores, f"{streams} streams x {blocks} blocks of {B} frames, one stream per thread, {cores} threads, {sec:.2f} s"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import numpy as np
+    import oracle
+    desc, S, B, n_per_gpu, hrir = WORKLOADS[args.workload]
+    pcm, rate = hrir_pcm_cpu(hrir)
+    l_idx, r_idx = hesuvi14_cpu(S)
+    taps = pcm.shape[1]
+    P = -(-taps // B)
+    h = np.zeros((S, 2, taps), np.float32)
+    for s in range(S):
+        h[s, 0], h[s, 1] = pcm[l_idx[s]], pcm[r_idx[s]]
+    cores = oracle.max_threads()
+    streams = max(cores * 4, 8)
+    batch = oracle.CpuBatch(streams, S, B, h)
+    # size the per-step sample so K steps end within a few minutes even for long BRIRs
+    blocks_per_step = 8      # amortises the per-step thread start-up over ~10 ms of work
+    pilot, _ = batch.step(blocks_per_step, cores)
+    total_est = pilot * (args.steps + args.warmup)
+    while total_est > 150 and streams > cores:
+        streams //= 2
+        batch = oracle.CpuBatch(streams, S, B, h)
+        pilot, _ = batch.step(blocks_per_step, cores)
+        total_est = pilot * (args.steps + args.warmup)
+    for _ in range(args.warmup):
+        batch.step(blocks_per_step, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        sec, _ = batch.step(blocks_per_step, cores)
+        t += sec
+    value = streams * blocks_per_step * args.steps * (B / FS) / t
+    sample = f"{streams} streams x {blocks_per_step} blocks of {B} frames per step, one stream per thread, {cores} threads"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "speakers": S, "block": B, "partitions": P, "taps": taps,
+                   "note": "reference algorithm (one ConvolutionEngine per speaker x ear, zvmul+zvadd passes) restated in C "
+                           "(oracle/airwave_oracle.c); the Swift/vDSP reference cannot run on Linux"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def hrir_pcm_cpu(name: str):
+    """hrir_pcm without touching the CUDA library (reference arm)."""
+    import numpy as np
+    import oracle
+    if name == "synthetic65536":
+        rng = np.random.default_rng(1)
+        n = np.arange(65536)
+        pcm = (0.05 * rng.standard_normal((14, 65536)) * np.exp(-n / (0.25 * FS))).astype(np.float32)
+        pcm[:, 190] += 0.5
+        return pcm, FS
+    w = oracle.load_wav(os.path.join(GOLDEN, "hrtf", name + ".wav"))
+    return w.audioData, w.sampleRate
+
+
+def hesuvi14_cpu(S: int):
+    import oracle
+    lay = oracle.InputLayout.detect(S)
+    m = oracle.HRIRChannelMap.hesuvi14Channel(lay.channels)
+    return [m.getIndices(s)[0] for s in lay.channels], [m.getIndices(s)[1] for s in lay.channels]
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import airwave_b200 as aw
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or aw.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    desc, S, B, n, hrir = WORKLOADS[args.workload]
+    if args.streams > 0:
+        n = args.streams
+    pcm, rate = hrir_pcm(hrir)
+    l_idx, r_idx = speaker_maps(S)
+    bank = aw.HRIRBank(pcm, rate, FS, l_idx, r_idx, B, device=local)
+    P, taps = bank.partitions, bank.taps
+    e2e_frames = max(B, min(4096, args.e2e_frames // B * B))
+    eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=e2e_frames, max_partitions=P, device=local, pipelined=True)
+    eng.set_bank(bank)
+    stream = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
+
+    # device-resident synthetic input: a time-contiguous ring of R blocks per (stream, speaker)
+    R = 8
+    x = torch.empty((n, S, R * B), dtype=torch.float32, device=f"cuda:{local}")
+    y = torch.empty((n, 2, B), dtype=torch.float32, device=f"cuda:{local}")
+    aw._lib.check(aw.lib().aw_synth_fill_device(local, x.data_ptr(), rank * n, n, S, 0, R * B, SEED, None))
+    torch.cuda.synchronize()
+    xp, yp = x.data_ptr(), y.data_ptr()
+
+    def step(j: int):
+        eng.process_device(xp + 4 * (j % R) * B, S * R * B, R * B, yp, 2 * B, B, B)
+
+    W = max(args.warmup, 3)
+    for j in range(W):
+        step(j)
+    torch.cuda.synchronize()
+
+    K = args.steps
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    sampler = ClockSampler(local)
+    c0 = eng.counters()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    events[0].record(stream)
+    for j in range(K):
+        step(W + j)
+        events[j + 1].record(stream)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    clocks = sampler.stop()
+    c1 = eng.counters()
+    elapsed_ms = events[0].elapsed_time(events[K])
+    per_step = sorted(events[j].elapsed_time(events[j + 1]) for j in range(K))
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms_max = float(t.item())
+    value = world * n * K * (B / FS) / (elapsed_ms_max * 1e-3)
+
+    # per-kernel pass (same steps, events around every launch) -> roofline of the dominant kernel
+    prof_steps = min(K, 200)
+    eng.profile_begin(prof_steps)
+    for j in range(prof_steps):
+        step(W + K + j)
+    prof = eng.profile_end()
+    peak, peak_src = measured_peaks()
+    mac_ms = prof["fdl_cmac"]["ms"] / max(prof["fdl_cmac"]["launches"], 1)
+    mac_bytes = n * (8 * S * B * P + 16 * B)          # FDL slots read once (P per speaker) + acc written
+    achieved = mac_bytes / (mac_ms * 1e-3) / 1e9
+    step_bytes = n * algorithmic_bytes(S, B, P)
+    step_ms = elapsed_ms_max / K
+    kernels_ms = {k: v["ms"] / max(v["launches"], 1) for k, v in prof.items()}
+
+    # end-to-end: pinned host buffers, every step's input H2D and output D2H inside the timed region
+    F = e2e_frames
+    n_bufs = 3
+    hin = [aw.PinnedBuffer((n, S, F)) for _ in range(n_bufs)]
+    hout = [aw.PinnedBuffer((n, 2, F)) for _ in range(n_bufs)]
+    stage = torch.empty((n, S, F), dtype=torch.float32, device=f"cuda:{local}")
+    for i, b in enumerate(hin):
+        aw._lib.check(aw.lib().aw_synth_fill_device(local, stage.data_ptr(), rank * n, n, S, i * F, F, SEED, None))
+        torch.cuda.synchronize()
+        b.array[...] = stage.cpu().numpy()
+    del stage
+    e2e_steps = max(3, min(args.e2e_steps, 10_000))
+    for i in range(2):
+        eng.submit(hin[i % n_bufs].array.ctypes.data, hout[i % n_bufs].array.ctypes.data, F)
+    eng.wait()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.submit(hin[i % n_bufs].array.ctypes.data, hout[i % n_bufs].array.ctypes.data, F)
+    eng.wait()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    checksum = float(hout[(e2e_steps - 1) % n_bufs].array[:, :, -1].astype("float64").sum())
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps * (F / FS) / float(te.item())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, sample = cpu_sample(S, B, pcm if rate == FS else pcm, l_idx, r_idx, args.cpu_seconds)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "streams_per_gpu": n, "speakers": S, "block": B, "partitions": P,
+                       "taps": taps, "step": f"one {B}-frame block for all streams (K2 input_rfft + K3 fdl_cmac + K4 irfft_out)",
+                       "l2": f"inputs larger than L2: the FDL working set read every step is {n * 8 * S * B * P / 1e6:.0f} MB (L2 = 126 MB)",
+                       "mac_tile": os.environ.get("AW_MAC_TILE", "auto")},
+            "roofline": {"bound": "hbm", "kernel": "k_fdl_cmac", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": mac_bytes, "kernel_ms": mac_ms},
+            "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
+                              "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "kernels_ms": kernels_ms},
+            "latency_ms": {"p50": per_step[len(per_step) // 2], "p99": per_step[min(len(per_step) - 1, int(0.99 * len(per_step)))],
+                           "max": per_step[-1]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * S * F * 4, "d2h_bytes_per_step": n * 2 * F * 4,
+                    "frames_per_step": F, "steps": e2e_steps, "timing": "host wall clock around aw_engine_submit..aw_engine_wait, "
+                    "synchronised on both sides, max over ranks; copies overlap kernels across steps (2 staging sets)",
+                    "checksum": checksum},
+            "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
+            "clocks": clocks,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
+    ap.add_argument("--e2e-frames", type=int, default=1024)
+    ap.add_argument("--e2e-steps", type=int, default=40)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -221,6 +221,11 @@ AW_API int aw_engine_reset(aw_engine *engine, int first, int count, int what);
 /* Counters since creation: kernels launched by this engine, blocks rendered, bytes copied H2D / D2H. */
 AW_API int aw_engine_counters(const aw_engine *engine, unsigned long long *kernel_launches, unsigned long long *blocks,
                               unsigned long long *h2d_bytes, unsigned long long *d2h_bytes);
+/* Per-kernel device timing for benchmarks: between begin and end, CUDA events bracket the three per-block kernels
+ * (K2 input_rfft, K3 fdl_cmac, K4 irfft_out) of up to `max_blocks` blocks on the engine's stream.  end() synchronises and
+ * returns the summed milliseconds and launch counts per kernel (index 0..2).  Not for the real-time path. */
+AW_API int aw_engine_profile_begin(aw_engine *engine, int max_blocks);
+AW_API int aw_engine_profile_end(aw_engine *engine, double *kernel_ms, unsigned long long *kernel_launches);
 /* Raw CUDA stream (cudaStream_t) the engine launches on, for event timing by the caller. */
 AW_API void *aw_engine_stream(const aw_engine *engine);
 /* Pinned host memory helpers for callers that cannot call cudaHostAlloc themselves. */

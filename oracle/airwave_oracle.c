@@ -930,3 +930,95 @@ OR_API double or_bench_render(int n_streams, int S, int B, const float *h, int t
     if (checksum) *checksum = sum;
     return t1 - t0;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Persistent CPU batch for bench.py --impl reference: engines are built once, every step
+ * renders `blocks` blocks for each of the sample's streams (one stream per thread at a time,
+ * all host threads).  Same structure as or_bench_render.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    int n_streams, S, B, ring_blocks, next_block;
+    or_conv_engine **L, **R;
+    or_rap **raps;
+    float *input;   /* [stream][ring_blocks][S][B], synthesised once */
+} or_batch;
+
+OR_API or_batch *or_batch_create(int n_streams, int S, int B, const float *h, int taps, int ring_blocks, uint32_t seed)
+{
+    or_batch *b = (or_batch *)calloc(1, sizeof(*b));
+    b->n_streams = n_streams; b->S = S; b->B = B; b->ring_blocks = ring_blocks;
+    b->L = (or_conv_engine **)calloc((size_t)n_streams * S, sizeof(void *));
+    b->R = (or_conv_engine **)calloc((size_t)n_streams * S, sizeof(void *));
+    b->raps = (or_rap **)calloc(n_streams, sizeof(void *));
+    for (int t = 0; t < n_streams; ++t) {
+        for (int s = 0; s < S; ++s) {
+            b->L[(size_t)t * S + s] = or_conv_create(h + ((size_t)s * 2 + 0) * taps, taps, B, NULL);
+            b->R[(size_t)t * S + s] = or_conv_create(h + ((size_t)s * 2 + 1) * taps, taps, B, NULL);
+        }
+        b->raps[t] = or_rap_create(b->L + (size_t)t * S, b->R + (size_t)t * S, S, B, B, 0);
+    }
+    const size_t per_stream = (size_t)ring_blocks * S * B;
+    b->input = (float *)malloc(sizeof(float) * per_stream * (size_t)n_streams);
+    for (int t = 0; t < n_streams; ++t)
+        for (int k = 0; k < ring_blocks; ++k)
+            for (int s = 0; s < S; ++s)
+                or_synth_fill(seed, (uint32_t)t, (uint32_t)s, (uint32_t)k * B, B, b->input + (size_t)t * per_stream + ((size_t)k * S + s) * B);
+    return b;
+}
+
+typedef struct { or_batch *b; int blocks; volatile int *next; double sum; } or_batch_job;
+
+static void *or_batch_worker(void *arg)
+{
+    or_batch_job *j = (or_batch_job *)arg;
+    or_batch *b = j->b;
+    const int S = b->S, B = b->B;
+    float *oL = (float *)malloc(sizeof(float) * B), *oR = (float *)malloc(sizeof(float) * B);
+    const float **ptrs = (const float **)malloc(sizeof(void *) * S);
+    const size_t per_stream = (size_t)b->ring_blocks * S * B;
+    double sum = 0;
+    for (;;) {
+        const int t = __sync_fetch_and_add(j->next, 1);
+        if (t >= b->n_streams) break;
+        for (int k = 0; k < j->blocks; ++k) {
+            const int rb = (b->next_block + k) % b->ring_blocks;
+            const float *in = b->input + (size_t)t * per_stream + (size_t)rb * S * B;
+            for (int s = 0; s < S; ++s) ptrs[s] = in + (size_t)s * B;
+            or_rap_process(b->raps[t], ptrs, oL, oR, B);
+            sum += (double)oL[B - 1] + (double)oR[0];
+        }
+    }
+    free(oL); free(oR); free((void *)ptrs);
+    j->sum = sum;
+    return NULL;
+}
+
+/* Renders `blocks` blocks for every stream with `threads` host threads; returns wall seconds. */
+OR_API double or_batch_step(or_batch *b, int blocks, int threads, double *checksum)
+{
+    if (threads < 1) threads = or_max_threads();
+    if (threads > 256) threads = 256;
+    pthread_t th[256]; or_batch_job jobs[256];
+    volatile int next = 0;
+    const double t0 = or_now();
+    for (int i = 0; i < threads; ++i) {
+        jobs[i] = (or_batch_job){b, blocks, &next, 0.0};
+        pthread_create(&th[i], NULL, or_batch_worker, &jobs[i]);
+    }
+    double sum = 0;
+    for (int i = 0; i < threads; ++i) { pthread_join(th[i], NULL); sum += jobs[i].sum; }
+    const double t1 = or_now();
+    b->next_block = (b->next_block + blocks) % b->ring_blocks;
+    if (checksum) *checksum = sum;
+    return t1 - t0;
+}
+
+OR_API void or_batch_destroy(or_batch *b)
+{
+    if (!b) return;
+    for (int t = 0; t < b->n_streams; ++t) {
+        or_rap_destroy(b->raps[t]);
+        for (int s = 0; s < b->S; ++s) { or_conv_destroy(b->L[(size_t)t * b->S + s]); or_conv_destroy(b->R[(size_t)t * b->S + s]); }
+    }
+    free(b->L); free(b->R); free(b->raps); free(b->input); free(b);
+}

@@ -19,7 +19,7 @@ __all__ = [
     "RealtimeAudioProcessor", "resample_high_quality", "resample_output_count",
     "biquad_make", "BiquadCoefficientError", "ParametricEqualizerState",
     "ParametricEqualizerProcessor", "ParametricEqualizerPreparationError",
-    "direct_conv_f64", "synth_fill", "synth_block", "bench_render", "max_threads",
+    "direct_conv_f64", "synth_fill", "synth_block", "bench_render", "max_threads", "CpuBatch",
 ]
 
 
@@ -80,6 +80,11 @@ def lib() -> C.CDLL:
         L.or_bench_render.restype = C.c_double
         L.or_bench_render.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_uint32, dp]
         L.or_max_threads.restype = C.c_int
+        L.or_batch_create.restype = vp
+        L.or_batch_create.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_uint32]
+        L.or_batch_step.restype = C.c_double
+        L.or_batch_step.argtypes = [vp, C.c_int, C.c_int, dp]
+        L.or_batch_destroy.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -397,3 +402,22 @@ def bench_render(n_streams: int, S: int, B: int, h, blocks: int, threads: int = 
 
 def max_threads() -> int:
     return lib().or_max_threads()
+
+
+class CpuBatch:
+    """Persistent reference-structured CPU render of a bounded sample of streams (bench.py --impl reference)."""
+
+    def __init__(self, n_streams: int, S: int, B: int, h, ring_blocks: int = 8, seed: int = 0x41495257):
+        h = _f32(h)
+        self.n_streams, self.S, self.B = n_streams, S, B
+        self._h = lib().or_batch_create(n_streams, S, B, _fp(h), h.shape[2], ring_blocks, seed)
+
+    def step(self, blocks: int = 1, threads: int = 0):
+        chk = C.c_double()
+        sec = lib().or_batch_step(self._h, blocks, threads, C.byref(chk))
+        return sec, chk.value
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().or_batch_destroy(self._h)
+            self._h = None
