@@ -333,6 +333,11 @@ class BinauralEngine:
         L.check(L.lib().aw_engine_counters(self._h, *[C.byref(x) for x in v]))
         return dict(kernel_launches=v[0].value, blocks=v[1].value, h2d_bytes=v[2].value, d2h_bytes=v[3].value)
 
+    def plan(self) -> dict:
+        f, m, p = C.c_int(), C.c_int(), C.c_int()
+        L.check(L.lib().aw_engine_plan(self._h, C.byref(f), C.byref(m), C.byref(p)))
+        return dict(fused_tile=f.value, mac_tile=m.value, partitions_cap=p.value)
+
     def profile_begin(self, max_blocks: int) -> None:
         L.check(L.lib().aw_engine_profile_begin(self._h, max_blocks))
 
@@ -340,8 +345,8 @@ class BinauralEngine:
         ms = (C.c_double * 3)()
         cnt = (C.c_ulonglong * 3)()
         L.check(L.lib().aw_engine_profile_end(self._h, ms, cnt))
-        names = ["input_rfft", "fdl_cmac", "irfft_out"]
-        return {n: dict(ms=ms[i], launches=cnt[i]) for i, n in enumerate(names)}
+        names = ["fused", "-", "-"] if self.plan()["fused_tile"] > 0 else ["input_rfft", "fdl_cmac", "irfft_out"]
+        return {n: dict(ms=ms[i], launches=cnt[i]) for i, n in enumerate(names) if n != "-"}
 
     @property
     def cuda_stream(self) -> int:

@@ -128,6 +128,8 @@ struct aw_engine {
     aw_engine_config cfg{};
     int n = 0, S = 0, B = 0, log2m = 0, maxFrames = 0, P_cap = 0, fifoCap = 0;
     int macTile = 0;
+    int fusedTile = 0;             // 0 = split path (K2, K3, K4), else streams per CTA of the fused kernel
+    int numSMs = 148;
     const float2 *d_tw = nullptr;
     float2 *d_fdl = nullptr;
     float *d_fdl_ny = nullptr, *d_overlap = nullptr, *d_pending = nullptr, *d_fifo = nullptr;
@@ -410,12 +412,19 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
         cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
         if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
-        AW_LAUNCH(e, launch_input_rfft(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, e->d_tw, e->stream));
-        if (prof) cudaEventRecord(ev[1], e->stream);
-        AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, b->d_bank, e->d_acc, e->macTile, e->stream));
-        if (prof) cudaEventRecord(ev[2], e->stream);
-        AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, b->d_ny, out, e->d_tw, e->stream));
-        if (prof) cudaEventRecord(ev[3], e->stream);
+        if (e->fusedTile > 0) {
+            // K2 + K3 + K4 in one kernel; events 0..1 bracket it, 1..3 collapse to zero-length intervals
+            AW_LAUNCH(e, launch_fused(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
+                                      e->d_tw, e->fusedTile, e->stream));
+            if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
+        } else {
+            AW_LAUNCH(e, launch_input_rfft(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, e->d_tw, e->stream));
+            if (prof) cudaEventRecord(ev[1], e->stream);
+            AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, b->d_bank, e->d_acc, e->macTile, e->stream));
+            if (prof) cudaEventRecord(ev[2], e->stream);
+            AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, b->d_ny, out, e->d_tw, e->stream));
+            if (prof) cudaEventRecord(ev[3], e->stream);
+        }
     }
     ++e->blocks;
     return AW_OK;
@@ -812,7 +821,34 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
     const char *tile_env = getenv("AW_MAC_TILE");
     e->macTile = tile_env ? atoi(tile_env) : 0;
     if (!(e->macTile == 1 || e->macTile == 2 || e->macTile == 4 || e->macTile == 8))
-        e->macTile = e->n >= 2048 ? 4 : (e->n >= 512 ? 2 : 1);
+        e->macTile = e->n >= 1024 ? 2 : 1;
+    {
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, config->device) == cudaSuccess) e->numSMs = prop.multiProcessorCount;
+    }
+    // fused-kernel plan: the CTA owns whole streams, so the grid is n/T CTAs; prefer the largest tile (most filter
+    // reuse) that still fits in ONE wave of resident CTAs, else the tile with the least wave-quantisation loss.
+    e->fusedTile = 0;
+    const char *fused_env = getenv("AW_FUSED_TILE");   // 0 forces the split path, 1/2/4 force a tile
+    if (fused_supported(e->log2m) && !(fused_env && atoi(fused_env) == 0)) {
+        int forced = fused_env ? atoi(fused_env) : -1;
+        if (forced == 1 || forced == 2 || forced == 4) e->fusedTile = forced;
+        else {
+            double best = 0;
+            const int tiles[3] = {4, 2, 1};
+            for (int T : tiles) {
+                const int bps = fused_blocks_per_sm(e->log2m, T);
+                if (bps <= 0) continue;
+                const double slots = (double)bps * e->numSMs;
+                const double ctas = (double)((e->n + T - 1) / T);
+                const double waves = ctas / slots;
+                const double eff = waves / std::ceil(waves);            // wave-quantisation efficiency
+                const double reuse = 1.0 / (1.0 + 0.5 / T);             // filter traffic through L2 costs ~0.5/T of the FDL stream
+                const double score = eff * reuse * (waves <= 1.0 ? 1.0 : 0.9);
+                if (score > best) { best = score; e->fusedTile = T; }
+            }
+        }
+    }
     if (config->max_partitions > 0) {
         rc = alloc_fdl(e, config->max_partitions);
         if (rc != AW_OK) return fail(rc);
@@ -1101,6 +1137,15 @@ extern "C" int aw_engine_counters(const aw_engine *e, unsigned long long *kernel
     if (blocks) *blocks = e->blocks;
     if (h2d_bytes) *h2d_bytes = e->h2dBytes;
     if (d2h_bytes) *d2h_bytes = e->d2hBytes;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_plan(const aw_engine *e, int *fused_tile, int *mac_tile, int *partitions_cap)
+{
+    if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
+    if (fused_tile) *fused_tile = e->fusedTile;
+    if (mac_tile) *mac_tile = e->macTile;
+    if (partitions_cap) *partitions_cap = e->P_cap;
     return AW_OK;
 }
 

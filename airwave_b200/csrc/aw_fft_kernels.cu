@@ -1,0 +1,630 @@
+// aw_fft_kernels.cu — FFT-bearing kernels built on the register-radix core (aw_fft_reg.cuh):
+//
+//   K1 k_bank_build<LOG2M>   partition + zero-pad + forward real FFT of every HRIR   (ConvolutionEngine.swift:143-182)
+//   K2 k_input_rfft<LOG2M>   [prev | cur] frame -> forward real FFT -> FDL head slot  (ConvolutionEngine.swift:237-264)
+//   K4 k_irfft_out<LOG2M>    Nyquist sum + inverse real FFT + overlap-save discard    (ConvolutionEngine.swift:353-366)
+//   KF k_fused<LOG2M, T>     K2 + K3 + K4 for a tile of T streams in ONE kernel: the spectra of the tile are
+//                            produced, the FDL is streamed exactly once with the accumulators in registers,
+//                            and the two ear spectra go straight through the inverse transform — no
+//                            intermediate (acc) ever reaches HBM.  Used for 64 <= B <= 512.
+//
+// Thread organisation: a transform of M = B complex points is done by G = M/16 threads holding 16 values each;
+// a CTA runs NF transforms side by side.  In the fused kernel THREADS = B/2 (one bin pair per thread in the MAC
+// phase) which makes NF = 8 for every supported B.
+#include <stdint.h>
+
+#include "aw_fft_reg.cuh"
+#include "aw_kernels.h"
+
+namespace aw {
+
+using namespace awfft;
+
+// ------------------------------------------------------------------------------------------------
+// building blocks
+// ------------------------------------------------------------------------------------------------
+template <int LOG2M, int P>
+__device__ __forceinline__ void smem_load(const float2 *buf, float2 (&v)[RegFft<LOG2M>::E], int t)
+{
+#pragma unroll
+    for (int e = 0; e < RegFft<LOG2M>::E; ++e) v[e] = buf[pad16(RegFft<LOG2M>::template load_index<P>(t, e))];
+}
+
+template <int LOG2M, int P>
+__device__ __forceinline__ void smem_store(float2 *buf, const float2 (&v)[RegFft<LOG2M>::E], int t)
+{
+#pragma unroll
+    for (int e = 0; e < RegFft<LOG2M>::E; ++e) buf[pad16(RegFft<LOG2M>::template store_index<P>(t, e))] = v[e];
+}
+
+// Passes [P, LAST] entirely in shared memory (in place); every thread of the CTA must call it.
+template <int LOG2M, int P, int LAST>
+struct SmemPasses {
+    __device__ __forceinline__ static void run(float2 *buf, const float2 *tw, int t)
+    {
+        if constexpr (P <= LAST) {
+            float2 v[RegFft<LOG2M>::E];
+            smem_load<LOG2M, P>(buf, v, t);
+            __syncthreads();
+            RegFft<LOG2M>::template compute<P>(v, tw, t);
+            smem_store<LOG2M, P>(buf, v, t);
+            __syncthreads();
+            SmemPasses<LOG2M, P + 1, LAST>::run(buf, tw, t);
+        }
+    }
+};
+
+// Forward real FFT of one frame.  `load(i)` returns z[i] = x[2i] + i*x[2i+1] of the frame (i < M); on return the
+// padded buffer holds Z and (after the trailing barrier) `emit(k, X)` has been called by the owning threads for
+// k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
+template <int LOG2M, class Load, class Emit, class EmitNy>
+__device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int t, bool active, Load load, Emit emit, EmitNy emit_ny)
+{
+    using F = RegFft<LOG2M>;
+    constexpr int M = F::M;
+    {
+        float2 v[F::E];
+#pragma unroll
+        for (int e = 0; e < F::E; ++e) v[e] = active ? load(F::template load_index<0>(t, e), e) : make_float2(0.f, 0.f);
+        F::template compute<0>(v, tw, t);
+        smem_store<LOG2M, 0>(buf, v, t);
+    }
+    __syncthreads();
+    SmemPasses<LOG2M, 1, F::PASSES - 1>::run(buf, tw, t);
+    if (active) {
+        for (int k = t; k <= M / 2; k += F::G) {
+            if (k == 0) {
+                const float2 z0 = buf[0];
+                emit(0, make_float2(2.0f * (z0.x + z0.y), 0.0f));
+                emit_ny(2.0f * (z0.x - z0.y));
+            } else {
+                const int j = M - k;
+                const float2 a = buf[pad16(k)], b = buf[pad16(j)];
+                const float er = a.x + b.x, ei = a.y - b.y;   // E = Z[k] + conj(Z[M-k])
+                const float dr = a.x - b.x, di = a.y + b.y;   // D = Z[k] - conj(Z[M-k])
+                const float2 w = tw[k];                       // exp(-2*pi*i*k/N)
+                const float tr = w.x * dr - w.y * di, ti = w.x * di + w.y * dr;
+                emit(k, make_float2(er + ti, ei - tr));
+                if (j != k) emit(j, make_float2(er - ti, -ei - tr));
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Inverse real FFT: the padded buffer holds the packed spectrum acc[0..M) (acc[0].x = DC) and ny the Nyquist value;
+// `emit(i, x0, x1)` receives the time samples x[2i], x[2i+1] for i in [M/2, M) — the overlap-save "second half".
+// All threads of the CTA must call it (barriers); `active` masks the stores only.
+template <int LOG2M, class Emit>
+__device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float2 *tw, int t, bool active, Emit emit)
+{
+    using F = RegFft<LOG2M>;
+    constexpr int M = F::M;
+    // inverse split, in place; stores conj(Z) so that the forward passes compute conj(IFFT(Z))
+    for (int k = t; k <= M / 2; k += F::G) {
+        if (k == 0) {
+            const float dc = buf[0].x;
+            buf[0] = make_float2(dc + ny, -(dc - ny));
+        } else {
+            const int j = M - k;
+            const float2 a = buf[pad16(k)], b = buf[pad16(j)];
+            const float er = a.x + b.x, ei = a.y - b.y;
+            const float dr = a.x - b.x, di = a.y + b.y;
+            const float2 w = make_float2(tw[k].x, -tw[k].y);
+            const float tr = w.x * dr - w.y * di, ti = w.x * di + w.y * dr;
+            buf[pad16(k)] = make_float2(er - ti, -(ei + tr));
+            if (j != k) buf[pad16(j)] = make_float2(er + ti, -(-ei + tr));
+        }
+    }
+    __syncthreads();
+    SmemPasses<LOG2M, 0, F::PASSES - 2>::run(buf, tw, t);
+    {
+        constexpr int P = F::PASSES - 1;
+        float2 v[F::E];
+        smem_load<LOG2M, P>(buf, v, t);
+        F::template compute<P>(v, tw, t);
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) {
+                const int i = F::template store_index<P>(t, e);
+                if (i >= M / 2) emit(i - M / 2, v[e].x, -v[e].y);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ float group_sum(float v, int width)   // deterministic butterfly sum over `width` (<= 32) lanes
+{
+    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Nyquist product sum for one (stream, ear): sum_{s,p} fdl_ny[stream][s][(head+p)%P] * bank_ny[s][p][ear], computed by
+// the G threads of a transform.  part_s: G floats of scratch for this transform.  Result valid in every thread after
+// the two barriers inside.
+template <int G>
+__device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fdl_ny, const float *bank_ny, int stream, int ear,
+                                             bool active, int t, float *part_s)
+{
+    float sum = 0.f;
+    if (active) {
+        const int terms = g.S * g.P;
+        for (int i = t; i < terms; i += G) {
+            const int s = i / g.P, p = i - s * g.P;
+            int slot = g.head + p;
+            if (slot >= g.P) slot -= g.P;
+            sum = fmaf(fdl_ny[((size_t)stream * g.Se + s) * g.P_cap + slot], bank_ny[(size_t)i * 2 + ear], sum);
+        }
+    }
+    if constexpr (G <= 32) {
+        return group_sum(sum, G);
+    } else {
+        part_s[t] = sum;
+        __syncthreads();
+        float acc = 0.f;
+        if (t < 32) {
+            for (int i = t; i < G; i += 32) acc += part_s[i];
+        }
+        acc = group_sum(acc, 32);
+        if (t == 0) part_s[0] = acc;
+        __syncthreads();
+        return part_s[0];
+    }
+}
+
+template <int LOG2M>
+struct Geo {
+    using F = RegFft<LOG2M>;
+    static constexpr int M = F::M, G = F::G;
+    static constexpr int SA_THREADS = G > 128 ? G : 128;      // stand-alone K1/K2/K4
+    static constexpr int SA_NF = SA_THREADS / G;
+    static constexpr int PS = PaddedSize<LOG2M>::value;
+    static constexpr size_t sa_smem = (size_t)(M + SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
+};
+
+// ------------------------------------------------------------------------------------------------
+// K2  input_rfft
+// ------------------------------------------------------------------------------------------------
+struct InputRfftArgs {
+    BlockGeom g;
+    StridedIn cur, prev;
+    float *overlap_save;
+    float2 *fdl;
+    float *fdl_ny;
+    const float2 *tw;
+};
+
+template <int LOG2M>
+__global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_input_rfft(const InputRfftArgs a)
+{
+    using Gm = Geo<LOG2M>;
+    constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufs = tw + M;
+    const int tid = threadIdx.x, f = tid / G, t = tid % G;
+    for (int k = tid; k < M; k += Gm::SA_THREADS) tw[k] = a.tw[k];
+    __syncthreads();
+    const int job = blockIdx.x * NF + f;
+    const bool active = job < a.g.n_streams * a.g.S;
+    const int ls = active ? job / a.g.S : 0, s = active ? job - ls * a.g.S : 0;
+    const int stream = a.g.first_stream + ls;
+    const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
+    const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
+    float *ov = a.overlap_save ? a.overlap_save + ((size_t)stream * a.g.Se + s) * M : nullptr;
+    const size_t row = ((size_t)stream * a.g.Se + s) * a.g.P_cap + a.g.head;
+    float2 *dst = a.fdl + row * M;
+    float *dst_ny = a.fdl_ny + row;
+    forward_frame<LOG2M>(
+        bufs + (size_t)f * Gm::PS, tw, t, active,
+        [&](int i, int) -> float2 {   // frame = [previous block | current block]  (:237-248)
+            if (i < M / 2) return *reinterpret_cast<const float2 *>(prev + 2 * i);
+            const float2 v = *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2));
+            if (ov) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v;   // inputOverlapBuffer <- current block (:243);
+            return v;                                                          // same thread read this address as `prev`
+        },
+        [&](int k, float2 x) { dst[k] = x; },       // FDL[head] <- spectrum (:256-264)
+        [&](float ny) { *dst_ny = ny; });
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1  bank_build
+// ------------------------------------------------------------------------------------------------
+struct BankArgs {
+    const float *ir;   // [S][2][taps]
+    int S, taps, B, P;
+    float4 *bank;
+    float *bank_ny;
+    const float2 *tw;
+};
+
+template <int LOG2M>
+__global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_bank_build(const BankArgs a)
+{
+    using Gm = Geo<LOG2M>;
+    constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufs = tw + M;
+    const int tid = threadIdx.x, f = tid / G, t = tid % G;
+    for (int k = tid; k < M; k += Gm::SA_THREADS) tw[k] = a.tw[k];
+    __syncthreads();
+    const int job = blockIdx.x * NF + f;   // (s*2 + ear)*P + p
+    const bool active = job < a.S * 2 * a.P;
+    const int se = active ? job / a.P : 0, p = active ? job - se * a.P : 0;
+    const float *h = a.ir + (size_t)se * a.taps;
+    const float scale = 0.25f / (float)(2 * M);   // ConvolutionEngine.swift:356, folded into the bank (exact: power of two)
+    float *dst = reinterpret_cast<float *>(a.bank + ((size_t)(se >> 1) * a.P + p) * M) + 2 * (se & 1);
+    float *dst_ny = a.bank_ny + ((size_t)(se >> 1) * a.P + p) * 2 + (se & 1);
+    forward_frame<LOG2M>(
+        bufs + (size_t)f * Gm::PS, tw, t, active,
+        [&](int i, int) -> float2 {   // h[pB .. (p+1)B) || 0_B  (:145-155)
+            float2 v = make_float2(0.f, 0.f);
+            if (i < M / 2) {
+                const int t0 = p * M + 2 * i;
+                if (t0 < a.taps) v.x = h[t0];
+                if (t0 + 1 < a.taps) v.y = h[t0 + 1];
+            }
+            return v;
+        },
+        [&](int k, float2 x) { dst[4 * k] = x.x * scale; dst[4 * k + 1] = x.y * scale; },
+        [&](float ny) { *dst_ny = ny * scale; });
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4  irfft_out
+// ------------------------------------------------------------------------------------------------
+struct IrfftArgs {
+    BlockGeom g;
+    const float2 *acc;
+    const float *fdl_ny;
+    const float *bank_ny;
+    StridedOut out;
+    const float2 *tw;
+};
+
+__device__ __forceinline__ void store_pair(const StridedOut &o, float *row, int i2, float x0, float x1)
+{
+    if (o.ring_cap > 0) {
+        int p0 = o.ring_start + i2;
+        if (p0 >= o.ring_cap) p0 -= o.ring_cap;
+        int p1 = p0 + 1;
+        if (p1 >= o.ring_cap) p1 -= o.ring_cap;
+        row[p0] = x0;
+        row[p1] = x1;
+    } else if ((reinterpret_cast<uintptr_t>(row + i2) & 7u) == 0) {
+        *reinterpret_cast<float2 *>(row + i2) = make_float2(x0, x1);
+    } else {
+        row[i2] = x0;
+        row[i2 + 1] = x1;
+    }
+}
+
+template <int LOG2M>
+__global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const IrfftArgs a)
+{
+    using Gm = Geo<LOG2M>;
+    constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufs = tw + M;
+    float *part = reinterpret_cast<float *>(bufs + (size_t)NF * Gm::PS);
+    const int tid = threadIdx.x, f = tid / G, t = tid % G;
+    for (int k = tid; k < M; k += Gm::SA_THREADS) tw[k] = a.tw[k];
+    const int job = blockIdx.x * NF + f;   // (local stream, ear)
+    const bool active = job < a.g.n_streams * 2;
+    const int stream = a.g.first_stream + (active ? job >> 1 : 0), ear = job & 1;
+    float2 *buf = bufs + (size_t)f * Gm::PS;
+    if (active) {
+        const float2 *src = a.acc + ((size_t)stream * 2 + ear) * M;
+        for (int k = t; k < M; k += G) buf[pad16(k)] = src[k];
+    }
+    __syncthreads();
+    const float ny = nyquist_sum<G>(a.g, a.fdl_ny, a.bank_ny, stream, ear, active, t, part + (size_t)f * G);
+    float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
+    inverse_frame<LOG2M>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
+}
+
+// ------------------------------------------------------------------------------------------------
+// KF  fused block kernel: K2 + K3 + K4 for T streams per CTA
+// ------------------------------------------------------------------------------------------------
+struct FusedArgs {
+    BlockGeom g;
+    StridedIn cur, prev;
+    float *overlap_save;
+    float2 *fdl;
+    float *fdl_ny;
+    const float4 *bank;
+    const float *bank_ny;
+    StridedOut out;
+    const float2 *tw;
+};
+
+__device__ __forceinline__ float4 ldg_stream4(const float4 *p)
+{
+    float4 r;   // FDL history: read exactly once per block, keep it out of L1
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void cmac2f(float4 &acc, const float4 x, const float hr0, const float hi0, const float hr1, const float hi1)
+{
+    acc.x = fmaf(x.x, hr0, acc.x); acc.x = fmaf(-x.y, hi0, acc.x);
+    acc.y = fmaf(x.x, hi0, acc.y); acc.y = fmaf(x.y, hr0, acc.y);
+    acc.z = fmaf(x.z, hr1, acc.z); acc.z = fmaf(-x.w, hi1, acc.z);
+    acc.w = fmaf(x.z, hi1, acc.w); acc.w = fmaf(x.w, hr1, acc.w);
+}
+
+template <int LOG2M> struct FusedGeo {
+    static constexpr int M = 1 << LOG2M;
+    static constexpr int THREADS = M / 2;                // one bin pair per thread in the MAC phase
+    static constexpr int G = RegFft<LOG2M>::G;
+    static constexpr int NF = THREADS / G;               // = 8
+    static constexpr int PS = PaddedSize<LOG2M>::value;
+    static constexpr size_t smem = (size_t)(M + NF * PS) * sizeof(float2) + (size_t)THREADS * sizeof(float);
+};
+
+template <int LOG2M, int T, int MINB>
+__global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const FusedArgs a)
+{
+    using FG = FusedGeo<LOG2M>;
+    constexpr int M = FG::M, G = FG::G, NF = FG::NF, THREADS = FG::THREADS, halfB = M / 2;
+    static_assert(NF == 8 && 2 * T <= NF, "fused kernel geometry");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
+    float2 *bufs = tw + M;
+    float *part = reinterpret_cast<float *>(bufs + (size_t)NF * FG::PS);
+    const BlockGeom &g = a.g;
+    const int tid = threadIdx.x, f = tid / G, t = tid % G;
+    const int s0 = g.first_stream + blockIdx.x * T;
+    const int nvalid = min(T, g.first_stream + g.n_streams - s0);
+    for (int k = tid; k < M; k += THREADS) tw[k] = a.tw[k];
+    __syncthreads();
+
+    // ---- phase A: forward FFT of the T*S input frames, 8 at a time; spectra go to the FDL head slot ----------
+    const int nfft = T * g.S;
+    for (int base = 0; base < nfft; base += NF) {
+        const int idx = base + f;
+        const int ls = idx / g.S, s = idx - ls * g.S;
+        const bool active = idx < nfft && ls < nvalid;
+        const int stream = s0 + (active ? ls : 0);
+        const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
+        const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
+        float *ov = a.overlap_save ? a.overlap_save + ((size_t)stream * g.Se + s) * M : nullptr;
+        const size_t row = ((size_t)stream * g.Se + s) * g.P_cap + g.head;
+        float2 *dst = a.fdl + row * M;
+        float *dst_ny = a.fdl_ny + row;
+        forward_frame<LOG2M>(
+            bufs + (size_t)f * FG::PS, tw, t, active,
+            [&](int i, int) -> float2 {
+                if (i < M / 2) return *reinterpret_cast<const float2 *>(prev + 2 * i);
+                const float2 v = *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2));
+                if (ov) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v;
+                return v;
+            },
+            [&](int k, float2 x) { dst[k] = x; },
+            [&](float ny) { *dst_ny = ny; });
+    }
+    // the head slot written above is re-read below by other threads of this CTA: the barrier that ends
+    // forward_frame orders those global accesses within the block.
+
+    // ---- phase B: FDL multiply-accumulate over speakers and partitions, accumulators in registers ------------
+    const int jp = tid;   // bins 2*jp, 2*jp+1
+    const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+    const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
+    const float4 *fp[T];
+#pragma unroll
+    for (int u = 0; u < T; ++u) fp[u] = fdl4 + (size_t)(s0 + (u < nvalid ? u : 0)) * stream_stride + jp;
+    float4 aL[T], aR[T];
+#pragma unroll
+    for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
+    for (int s = 0; s < g.S; ++s) {
+        const float4 *bk = a.bank + (size_t)s * g.P * M + 2 * jp;
+        const size_t srow = (size_t)s * g.P_cap;
+        {   // p = 0: the slot this CTA has just written (coherent loads)
+            const float4 h0 = __ldg(bk), h1 = __ldg(bk + 1);
+            const size_t off = (srow + g.head) * halfB;
+#pragma unroll
+            for (int u = 0; u < T; ++u) {
+                const float4 x = *(fp[u] + off);
+                cmac2f(aL[u], x, h0.x, h0.y, h1.x, h1.y);
+                cmac2f(aR[u], x, h0.z, h0.w, h1.z, h1.w);
+            }
+        }
+        int slot = g.head + 1 == g.P ? 0 : g.head + 1;
+#pragma unroll 2
+        for (int p = 1; p < g.P; ++p) {
+            const float4 h0 = __ldg(bk + (size_t)p * M), h1 = __ldg(bk + (size_t)p * M + 1);
+            const size_t off = (srow + slot) * halfB;
+            float4 x[T];
+#pragma unroll
+            for (int u = 0; u < T; ++u) x[u] = ldg_stream4(fp[u] + off);
+#pragma unroll
+            for (int u = 0; u < T; ++u) {
+                cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
+                cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
+            }
+            slot = (slot + 1 == g.P) ? 0 : slot + 1;   // modulus is partitionCount, not a power of two (Q4)
+        }
+    }
+
+    // ---- phase C: accumulators -> shared, Nyquist sums, inverse FFT, overlap-save discard, output -------------
+#pragma unroll
+    for (int u = 0; u < T; ++u) {
+        float2 *bl = bufs + (size_t)(2 * u) * FG::PS, *br = bl + FG::PS;
+        bl[pad16(2 * jp)] = make_float2(aL[u].x, aL[u].y);
+        bl[pad16(2 * jp + 1)] = make_float2(aL[u].z, aL[u].w);
+        br[pad16(2 * jp)] = make_float2(aR[u].x, aR[u].y);
+        br[pad16(2 * jp + 1)] = make_float2(aR[u].z, aR[u].w);
+    }
+    __syncthreads();
+    {
+        const int ls = f >> 1, ear = f & 1;
+        const bool active = f < 2 * T && ls < nvalid;
+        const int stream = s0 + (active ? ls : 0);
+        const float ny = nyquist_sum<G>(g, a.fdl_ny, a.bank_ny, stream, ear, active, t, part + (size_t)f * G);
+        float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
+        inverse_frame<LOG2M>(bufs + (size_t)f * FG::PS, ny, tw, t, active,
+                             [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+#define AW_LOG2M_SWITCH(log2m, CALL)                                            \
+    switch (log2m) {                                                            \
+    case 2: CALL(2); break;   case 3: CALL(3); break;   case 4: CALL(4); break;   \
+    case 5: CALL(5); break;   case 6: CALL(6); break;   case 7: CALL(7); break;   \
+    case 8: CALL(8); break;   case 9: CALL(9); break;   case 10: CALL(10); break; \
+    case 11: CALL(11); break; case 12: CALL(12); break; case 13: CALL(13); break; \
+    default: return cudaErrorInvalidValue;                                      \
+    }
+
+cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl,
+                              float *fdl_ny, const float2 *tw, cudaStream_t st)
+{
+    const int jobs = g.n_streams * g.S;
+    if (jobs <= 0) return cudaSuccess;
+    InputRfftArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, tw};
+#define CALL(L) k_input_rfft<L><<<(jobs + Geo<L>::SA_NF - 1) / Geo<L>::SA_NF, Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+    AW_LOG2M_SWITCH(g.log2m, CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_irfft_out(const BlockGeom &g, const float2 *acc, const float *fdl_ny, const float *bank_ny,
+                             StridedOut out, const float2 *tw, cudaStream_t st)
+{
+    const int jobs = g.n_streams * 2;
+    if (jobs <= 0) return cudaSuccess;
+    IrfftArgs a{g, acc, fdl_ny, bank_ny, out, tw};
+#define CALL(L) k_irfft_out<L><<<(jobs + Geo<L>::SA_NF - 1) / Geo<L>::SA_NF, Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+    AW_LOG2M_SWITCH(g.log2m, CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bank_build(const float *ir, int S, int taps, int B, int log2m, int P, float4 *bank, float *bank_ny,
+                              const float2 *tw, cudaStream_t st)
+{
+    const int jobs = S * 2 * P;
+    BankArgs a{ir, S, taps, B, P, bank, bank_ny, tw};
+#define CALL(L) k_bank_build<L><<<(jobs + Geo<L>::SA_NF - 1) / Geo<L>::SA_NF, Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+    AW_LOG2M_SWITCH(log2m, CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+// ---- fused kernel: variants and planner ------------------------------------------------------------
+namespace {
+
+template <int LOG2M, int T, int MINB>
+cudaError_t launch_fused_t(const FusedArgs &a, int tiles, cudaStream_t st)
+{
+    k_fused<LOG2M, T, MINB><<<tiles, FusedGeo<LOG2M>::THREADS, FusedGeo<LOG2M>::smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// occupancy targets (CTAs/SM) the variants are compiled for: threads/CTA = B/2
+template <int LOG2M> struct FusedOcc;
+template <> struct FusedOcc<6> { static constexpr int t4 = 16, t2 = 24, t1 = 32; };   // 32 threads
+template <> struct FusedOcc<7> { static constexpr int t4 = 12, t2 = 16, t1 = 16; };   // 64 threads
+template <> struct FusedOcc<8> { static constexpr int t4 = 7, t2 = 9, t1 = 9; };      // 128 threads
+template <> struct FusedOcc<9> { static constexpr int t4 = 3, t2 = 4, t1 = 4; };      // 256 threads
+
+template <int LOG2M>
+cudaError_t launch_fused_l(const FusedArgs &a, int tile, cudaStream_t st)
+{
+    const int tiles = (a.g.n_streams + tile - 1) / tile;
+    switch (tile) {
+    case 4: return launch_fused_t<LOG2M, 4, FusedOcc<LOG2M>::t4>(a, tiles, st);
+    case 2: return launch_fused_t<LOG2M, 2, FusedOcc<LOG2M>::t2>(a, tiles, st);
+    case 1: return launch_fused_t<LOG2M, 1, FusedOcc<LOG2M>::t1>(a, tiles, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+template <int LOG2M, int T, int MINB>
+int fused_blocks_per_sm()
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<LOG2M, T, MINB>, FusedGeo<LOG2M>::THREADS, FusedGeo<LOG2M>::smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+template <int LOG2M>
+int fused_blocks_per_sm_l(int tile)
+{
+    switch (tile) {
+    case 4: return fused_blocks_per_sm<LOG2M, 4, FusedOcc<LOG2M>::t4>();
+    case 2: return fused_blocks_per_sm<LOG2M, 2, FusedOcc<LOG2M>::t2>();
+    case 1: return fused_blocks_per_sm<LOG2M, 1, FusedOcc<LOG2M>::t1>();
+    default: return 0;
+    }
+}
+
+}  // namespace
+
+bool fused_supported(int log2m) { return log2m >= 6 && log2m <= 9; }
+
+int fused_blocks_per_sm(int log2m, int tile)
+{
+    switch (log2m) {
+    case 6: return fused_blocks_per_sm_l<6>(tile);
+    case 7: return fused_blocks_per_sm_l<7>(tile);
+    case 8: return fused_blocks_per_sm_l<8>(tile);
+    case 9: return fused_blocks_per_sm_l<9>(tile);
+    default: return 0;
+    }
+}
+
+cudaError_t launch_fused(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
+                         const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, cudaStream_t st)
+{
+    if (g.n_streams <= 0) return cudaSuccess;
+    FusedArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, bank, bank_ny, out, tw};
+    switch (g.log2m) {
+    case 6: return launch_fused_l<6>(a, tile, st);
+    case 7: return launch_fused_l<7>(a, tile, st);
+    case 8: return launch_fused_l<8>(a, tile, st);
+    case 9: return launch_fused_l<9>(a, tile, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+size_t fft_smem_bytes(int log2m)
+{
+    size_t b = 0;
+#define CALL(L) b = Geo<L>::sa_smem
+    switch (log2m) {
+    case 2: CALL(2); break;   case 3: CALL(3); break;   case 4: CALL(4); break;   case 5: CALL(5); break;
+    case 6: CALL(6); break;   case 7: CALL(7); break;   case 8: CALL(8); break;   case 9: CALL(9); break;
+    case 10: CALL(10); break; case 11: CALL(11); break; case 12: CALL(12); break; case 13: CALL(13); break;
+    default: break;
+    }
+#undef CALL
+    return b;
+}
+
+cudaError_t configure_kernels(int log2m)
+{
+    cudaError_t e = cudaSuccess;
+#define CALL(L)                                                                                                              \
+    do {                                                                                                                     \
+        if (Geo<L>::sa_smem > 48 * 1024) {                                                                                   \
+            if ((e = cudaFuncSetAttribute(k_input_rfft<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e; \
+            if ((e = cudaFuncSetAttribute(k_irfft_out<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e;  \
+            if ((e = cudaFuncSetAttribute(k_bank_build<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e; \
+        }                                                                                                                    \
+    } while (0)
+    AW_LOG2M_SWITCH(log2m, CALL)
+#undef CALL
+    return e;
+}
+
+}  // namespace aw

@@ -18,105 +18,8 @@
 
 #include <stdint.h>
 
-#include "aw_fft.cuh"
 
 namespace aw {
-
-using namespace awfft;
-
-static constexpr int kFftThreads = 256;
-
-int fft_batch(int log2m)
-{
-    int nf = (4 * kFftThreads) >> log2m;   // one radix-4 butterfly per thread per stage
-    if (nf < 1) nf = 1;
-    if (nf > 8) nf = 8;                    // <= one warp per transform for the Nyquist reduction in K4
-    return nf;
-}
-
-size_t fft_smem_bytes(int log2m)
-{
-    const size_t M = (size_t)1 << log2m;
-    return (M + 2 * (size_t)fft_batch(log2m) * M) * sizeof(float2) + 8 * sizeof(float);
-}
-
-// ------------------------------------------------------------------------------------------------
-// K2  input_rfft
-// ------------------------------------------------------------------------------------------------
-struct InputRfftArgs {
-    BlockGeom g;
-    StridedIn cur, prev;
-    float *overlap_save;
-    float2 *fdl;
-    float *fdl_ny;
-    const float2 *tw;
-    int nf;
-};
-
-__global__ void __launch_bounds__(kFftThreads) k_input_rfft(const InputRfftArgs a)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int log2m = a.g.log2m, M = 1 << log2m, nf = a.nf, half = M >> 1;
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufA = tw + M;
-    float2 *bufB = bufA + (size_t)nf * M;
-    float *ny = reinterpret_cast<float *>(bufB + (size_t)nf * M);
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int total_jobs = a.g.n_streams * a.g.S;
-    const int job0 = blockIdx.x * nf;
-
-    for (int k = tid; k < M; k += nth) tw[k] = a.tw[k];
-    // frame = [previous block | current block], packed as z[n] = x[2n] + i*x[2n+1]  (:237-248)
-    for (int idx = tid; idx < nf * M; idx += nth) {
-        const int f = idx >> log2m, n = idx & (M - 1);
-        const int job = job0 + f;
-        float2 v = make_float2(0.f, 0.f);
-        if (job < total_jobs) {
-            const int stream = a.g.first_stream + job / a.g.S, s = job % a.g.S;
-            if (n < half) v = *reinterpret_cast<const float2 *>(a.prev.ptr + stream * a.prev.ss + s * a.prev.cs + 2 * n);
-            else v = *reinterpret_cast<const float2 *>(a.cur.ptr + stream * a.cur.ss + s * a.cur.cs + 2 * (n - half));
-        }
-        bufA[idx] = v;
-    }
-    __syncthreads();
-    if (a.overlap_save != nullptr) {   // inputOverlapBuffer <- current block  (:243)
-        for (int idx = tid; idx < nf * half; idx += nth) {
-            const int f = idx / half, n = idx - f * half;
-            const int job = job0 + f;
-            if (job < total_jobs) {
-                const int stream = a.g.first_stream + job / a.g.S, s = job % a.g.S;
-                *reinterpret_cast<float2 *>(a.overlap_save + ((size_t)stream * a.g.Se + s) * a.g.B + 2 * n) = bufA[(size_t)f * M + half + n];
-            }
-        }
-    }
-    float2 *z = cfft_batched<false>(bufA, bufB, tw, log2m, nf);
-    float2 *spec = (z == bufA) ? bufB : bufA;
-    const int per = half + 1;
-    for (int i = tid; i < nf * per; i += nth) split_forward(z, spec, ny, tw, log2m, i);
-    __syncthreads();
-    // FDL[head] <- spectrum  (:256-264)
-    for (int idx = tid; idx < nf * M; idx += nth) {
-        const int f = idx >> log2m, k = idx & (M - 1);
-        const int job = job0 + f;
-        if (job < total_jobs) {
-            const int stream = a.g.first_stream + job / a.g.S, s = job % a.g.S;
-            const size_t row = ((size_t)stream * a.g.Se + s) * a.g.P_cap + a.g.head;
-            a.fdl[row * M + k] = spec[idx];
-            if (k == 0) a.fdl_ny[row] = ny[f];
-        }
-    }
-}
-
-cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl,
-                              float *fdl_ny, const float2 *tw, cudaStream_t st)
-{
-    InputRfftArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, tw, fft_batch(g.log2m)};
-    const int jobs = g.n_streams * g.S;
-    const int grid = (jobs + a.nf - 1) / a.nf;
-    if (grid <= 0) return cudaSuccess;
-    k_input_rfft<<<grid, kFftThreads, fft_smem_bytes(g.log2m), st>>>(a);
-    return cudaGetLastError();
-}
 
 // ------------------------------------------------------------------------------------------------
 // K3  fdl_cmac — the bandwidth-bound core.  One thread owns two adjacent bins of T streams: the
@@ -205,157 +108,6 @@ cudaError_t launch_fdl_cmac(const BlockGeom &g, const float2 *fdl, const float4 
     case 8: k_fdl_cmac<8><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// K4  irfft_out
-// ------------------------------------------------------------------------------------------------
-struct IrfftArgs {
-    BlockGeom g;
-    const float2 *acc;
-    const float *fdl_ny;
-    const float *bank_ny;
-    StridedOut out;
-    const float2 *tw;
-    int nf;
-};
-
-__global__ void __launch_bounds__(kFftThreads) k_irfft_out(const IrfftArgs a)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int log2m = a.g.log2m, M = 1 << log2m, nf = a.nf, half = M >> 1;
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufA = tw + M;
-    float2 *bufB = bufA + (size_t)nf * M;
-    float *ny = reinterpret_cast<float *>(bufB + (size_t)nf * M);
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int total_jobs = a.g.n_streams * 2;   // (stream, ear)
-    const int job0 = blockIdx.x * nf;
-
-    for (int k = tid; k < M; k += nth) tw[k] = a.tw[k];
-    for (int idx = tid; idx < nf * M; idx += nth) {
-        const int f = idx >> log2m, k = idx & (M - 1);
-        const int job = job0 + f;
-        float2 v = make_float2(0.f, 0.f);
-        if (job < total_jobs) v = a.acc[((size_t)a.g.first_stream * 2 + job) * M + k];
-        bufA[idx] = v;
-    }
-    // Nyquist bin: imagp[0] products of ConvolutionEngine.swift:305,337, summed over partitions and speakers
-    {
-        const int warp = tid >> 5, lane = tid & 31;
-        if (warp < nf) {
-            const int job = job0 + warp;
-            float sum = 0.f;
-            if (job < total_jobs) {
-                const int stream = a.g.first_stream + (job >> 1), ear = job & 1;
-                const int terms = a.g.S * a.g.P;
-                for (int i = lane; i < terms; i += 32) {
-                    const int s = i / a.g.P, p = i - s * a.g.P;
-                    int slot = a.g.head + p;
-                    if (slot >= a.g.P) slot -= a.g.P;
-                    sum = fmaf(a.fdl_ny[((size_t)stream * a.g.Se + s) * a.g.P_cap + slot], a.bank_ny[(size_t)i * 2 + ear], sum);
-                }
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) ny[warp] = sum;
-        }
-    }
-    __syncthreads();
-    const int per = half + 1;
-    for (int i = tid; i < nf * per; i += nth) split_inverse(bufA, ny, bufB, tw, log2m, i);
-    __syncthreads();
-    float2 *z = cfft_batched<true>(bufB, bufA, tw, log2m, nf);
-    // valid output = second half of the frame (:366): x[B + i], i < B  <=>  z[M/2 + i/2].{x,y}
-    const int B = a.g.B;
-    for (int idx = tid; idx < nf * B; idx += nth) {
-        const int f = idx / B, i = idx - f * B;
-        const int job = job0 + f;
-        if (job < total_jobs) {
-            const int stream = a.g.first_stream + (job >> 1), ear = job & 1;
-            const float2 v = z[(size_t)f * M + half + (i >> 1)];
-            int pos = i;
-            if (a.out.ring_cap > 0) { pos = a.out.ring_start + i; if (pos >= a.out.ring_cap) pos -= a.out.ring_cap; }
-            a.out.ptr[stream * a.out.ss + ear * a.out.cs + pos] = (i & 1) ? v.y : v.x;
-        }
-    }
-}
-
-cudaError_t launch_irfft_out(const BlockGeom &g, const float2 *acc, const float *fdl_ny, const float *bank_ny,
-                             StridedOut out, const float2 *tw, cudaStream_t st)
-{
-    IrfftArgs a{g, acc, fdl_ny, bank_ny, out, tw, fft_batch(g.log2m)};
-    const int jobs = g.n_streams * 2;
-    const int grid = (jobs + a.nf - 1) / a.nf;
-    if (grid <= 0) return cudaSuccess;
-    k_irfft_out<<<grid, kFftThreads, fft_smem_bytes(g.log2m), st>>>(a);
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
-// K1  bank_build: h[pB .. (p+1)B) || 0_B  ->  rfft  ->  x 0.25/N  (exact power-of-two scaling)
-// ------------------------------------------------------------------------------------------------
-struct BankArgs {
-    const float *ir;   // [S][2][taps]
-    int S, taps, B, log2m, P, nf;
-    float4 *bank;
-    float *bank_ny;
-    const float2 *tw;
-};
-
-__global__ void __launch_bounds__(kFftThreads) k_bank_build(const BankArgs a)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int log2m = a.log2m, M = 1 << log2m, nf = a.nf, half = M >> 1;
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufA = tw + M;
-    float2 *bufB = bufA + (size_t)nf * M;
-    float *ny = reinterpret_cast<float *>(bufB + (size_t)nf * M);
-    const int tid = threadIdx.x, nth = blockDim.x;
-    const int total_jobs = a.S * 2 * a.P;   // job = (s*2 + ear)*P + p
-    const int job0 = blockIdx.x * nf;
-    for (int k = tid; k < M; k += nth) tw[k] = a.tw[k];
-    for (int idx = tid; idx < nf * M; idx += nth) {
-        const int f = idx >> log2m, n = idx & (M - 1);
-        const int job = job0 + f;
-        float2 v = make_float2(0.f, 0.f);
-        if (job < total_jobs && n < half) {
-            const int se = job / a.P, p = job - se * a.P;
-            const int t0 = p * a.B + 2 * n;
-            const float *h = a.ir + (size_t)se * a.taps;
-            if (t0 < a.taps) v.x = h[t0];
-            if (t0 + 1 < a.taps) v.y = h[t0 + 1];
-        }
-        bufA[idx] = v;
-    }
-    __syncthreads();
-    float2 *z = cfft_batched<false>(bufA, bufB, tw, log2m, nf);
-    float2 *spec = (z == bufA) ? bufB : bufA;
-    for (int i = tid; i < nf * (half + 1); i += nth) split_forward(z, spec, ny, tw, log2m, i);
-    __syncthreads();
-    const float scale = 0.25f / (float)(2 * a.B);   // ConvolutionEngine.swift:356, folded into the bank
-    for (int idx = tid; idx < nf * M; idx += nth) {
-        const int f = idx >> log2m, k = idx & (M - 1);
-        const int job = job0 + f;
-        if (job < total_jobs) {
-            const int se = job / a.P, p = job - se * a.P;
-            const int s = se >> 1, ear = se & 1;
-            float *dst = reinterpret_cast<float *>(a.bank + ((size_t)s * a.P + p) * a.B + k) + 2 * ear;
-            dst[0] = spec[idx].x * scale;
-            dst[1] = spec[idx].y * scale;
-            if (k == 0) a.bank_ny[((size_t)s * a.P + p) * 2 + ear] = ny[f] * scale;
-        }
-    }
-}
-
-cudaError_t launch_bank_build(const float *ir, int S, int taps, int B, int log2m, int P, float4 *bank, float *bank_ny,
-                              const float2 *tw, cudaStream_t st)
-{
-    BankArgs a{ir, S, taps, B, log2m, P, fft_batch(log2m), bank, bank_ny, tw};
-    const int jobs = S * 2 * P;
-    const int grid = (jobs + a.nf - 1) / a.nf;
-    k_bank_build<<<grid, kFftThreads, fft_smem_bytes(log2m), st>>>(a);
     return cudaGetLastError();
 }
 
@@ -617,17 +369,6 @@ cudaError_t launch_eq_reset(double *z, int first_stream, int n_streams, int voic
     const int grid = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
     k_eq_reset<<<grid, 256, 0, st>>>(z, first_stream, n_streams, voice_mask);
     return cudaGetLastError();
-}
-
-cudaError_t configure_kernels(int max_log2m)
-{
-    const int bytes = (int)fft_smem_bytes(max_log2m);
-    if (bytes <= 48 * 1024) return cudaSuccess;
-    cudaError_t e;
-    if ((e = cudaFuncSetAttribute(k_input_rfft, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_irfft_out, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(k_bank_build, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) != cudaSuccess) return e;
-    return cudaSuccess;
 }
 
 }  // namespace aw

@@ -73,8 +73,13 @@ struct EqLaunch {
 cudaError_t launch_eq(const EqLaunch &l, int max_filters, double *z, StridedOut io, cudaStream_t st);
 cudaError_t launch_eq_reset(double *z, int first_stream, int n_streams, int voice_mask, cudaStream_t st);
 
-int fft_batch(int log2m);                 // transforms per CTA used by K1/K2/K4
+// KF: K2 + K3 + K4 fused for a tile of `tile` (1, 2 or 4) streams per CTA; 64 <= B <= 512.
+bool fused_supported(int log2m);
+int fused_blocks_per_sm(int log2m, int tile);   // resident CTAs per SM of that variant (occupancy API)
+cudaError_t launch_fused(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
+                         const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, cudaStream_t st);
+
 size_t fft_smem_bytes(int log2m);
-cudaError_t configure_kernels(int max_log2m);   // opt in to > 48 KB dynamic shared memory
+cudaError_t configure_kernels(int log2m);   // opt in to > 48 KB dynamic shared memory for that transform size
 
 }  // namespace aw

@@ -287,8 +287,9 @@ def test_bank_errors_mirror_the_reference(aw):
     assert seven.getIndices("LFE") == (2, 2)
 
 
-def test_arbitrary_frame_counts_match_block_aligned_rendering(aw, hrtf_path):
-    """K7: the adapter only delays; the same samples come out for any callback size sequence."""
+def test_arbitrary_frame_counts_follow_the_reference_adapter(aw, hrtf_path):
+    """K7: ragged callback sizes go through pending/FIFO exactly like RealtimeAudioProcessor.swift:77-190 —
+    silence on underflow, growing latency — and carry the same samples as block-aligned rendering."""
     wav = aw.WAVLoader.load(hrtf_path("RoomSH1.0"))
     bank = aw.HRIRBank.from_wav(wav, 48000.0, aw.InputLayout.surround71(), 256)
     x = oracle.synth_block(SEED, [0, 1, 2], 8, 0, 8192)
@@ -297,16 +298,27 @@ def test_arbitrary_frame_counts_match_block_aligned_rendering(aw, hrtf_path):
     aligned = np.concatenate([a.process(x[:, :, i:i + 1024]) for i in range(0, 8192, 1024)], axis=2)
     b = aw.BinauralEngine(3, 8, 256, 48000.0, 4096)
     b.set_bank(bank)
-    sizes, pos, outs = [1, 255, 256, 257, 100, 4096, 33, 512, 1000, 1682], 0, []
+    wav_o = oracle.load_wav(hrtf_path("RoomSH1.0"))
+    raps = [oracle.RealtimeAudioProcessor(oracle.activate_preset(wav_o, 48000.0, oracle.InputLayout.surround71, 256), 256, 4096,
+                                          literalStereo=False) for _ in range(3)]
+    sizes, pos = [1, 255, 256, 257, 100, 4096, 33, 512, 1000, 1682], 0
+    zeros_seen = 0
     for n in sizes:
-        outs.append(b.process(x[:, :, pos:pos + n]))
+        got = b.process(x[:, :, pos:pos + n])
+        for i in range(3):
+            ol, orr = raps[i].process_channels([x[i, s, pos:pos + n] for s in range(8)])
+            assert np.abs(got[i, 0] - ol).max() <= 2e-6 and np.abs(got[i, 1] - orr).max() <= 2e-6, (n, i)
+            assert np.array_equal(got[i, 0] == 0, ol == 0)     # silence exactly where the reference underflows
+        zeros_seen += int((got[0, 0] == 0).sum())
         pos += n
-    assert pos == 8192
-    ragged = np.concatenate(outs, axis=2)
-    # the first call delivers 1 frame before any block exists -> 1 frame of silence, then a constant 1-frame latency
-    delay = 1
-    assert np.all(ragged[:, :, :delay] == 0)
-    assert np.array_equal(ragged[:, :, delay:], aligned[:, :, : 8192 - delay])
+    assert pos == 8192 and zeros_seen >= 1 + 100
+    # the adapter only delays: block k of the ragged run is bit-identical to block k of the aligned run
+    c = aw.BinauralEngine(3, 8, 256, 48000.0, 4096)
+    c.set_bank(bank)
+    first = c.process(x[:, :, :128])
+    assert np.all(first == 0)
+    rest = np.concatenate([c.process(x[:, :, 128 + i:128 + i + 1024]) for i in range(0, 4096, 1024)], axis=2)
+    assert np.array_equal(rest, aligned[:, :, :4096])   # 128 frames late, otherwise the very same samples
 
 
 def test_streams_are_independent_and_batch_size_does_not_change_results(aw, hrtf_path):
