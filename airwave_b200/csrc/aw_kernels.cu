@@ -22,96 +22,6 @@
 namespace aw {
 
 // ------------------------------------------------------------------------------------------------
-// K3  fdl_cmac — the bandwidth-bound core.  One thread owns two adjacent bins of T streams: the
-// filter values are loaded once into registers and reused for the T streams of the tile; the FDL
-// is read exactly once (float4 = 2 complex bins, fully coalesced); partial sums over partitions AND
-// speakers stay in registers, nothing intermediate is written.
-// ------------------------------------------------------------------------------------------------
-static constexpr int kMacThreads = 128;
-
-__device__ __forceinline__ float4 ldg_stream(const float4 *p)
-{
-    float4 r;   // FDL history is read once per block: do not allocate in L1
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ void cmac2(float4 &acc, const float4 x, const float hr0, const float hi0, const float hr1, const float hi1)
-{
-    acc.x = fmaf(x.x, hr0, acc.x); acc.x = fmaf(-x.y, hi0, acc.x);
-    acc.y = fmaf(x.x, hi0, acc.y); acc.y = fmaf(x.y, hr0, acc.y);
-    acc.z = fmaf(x.z, hr1, acc.z); acc.z = fmaf(-x.w, hi1, acc.z);
-    acc.w = fmaf(x.z, hi1, acc.w); acc.w = fmaf(x.w, hr1, acc.w);
-}
-
-template <int T>
-__global__ void __launch_bounds__(kMacThreads) k_fdl_cmac(const BlockGeom g, const float4 *__restrict__ fdl,
-                                                           const float4 *__restrict__ bank, float4 *__restrict__ acc)
-{
-    const int halfB = g.B >> 1;
-    const int chunks = (halfB + kMacThreads - 1) / kMacThreads;
-    const int tile = blockIdx.x / chunks, chunk = blockIdx.x - tile * chunks;
-    const int jp = chunk * kMacThreads + threadIdx.x;
-    if (jp >= halfB) return;
-    const int s0 = g.first_stream + tile * T;
-    const int last = g.first_stream + g.n_streams - 1;
-    const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
-    const float4 *fp[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) fp[t] = fdl + (size_t)min(s0 + t, last) * stream_stride + jp;
-    float4 aL[T], aR[T];
-#pragma unroll
-    for (int t = 0; t < T; ++t) { aL[t] = make_float4(0.f, 0.f, 0.f, 0.f); aR[t] = aL[t]; }
-
-    for (int s = 0; s < g.S; ++s) {
-        const float4 *bk = bank + (size_t)s * g.P * g.B + 2 * jp;
-        const size_t srow = (size_t)s * g.P_cap;
-        int slot = g.head;
-#pragma unroll 2
-        for (int p = 0; p < g.P; ++p) {
-            const float4 h0 = __ldg(bk + (size_t)p * g.B);
-            const float4 h1 = __ldg(bk + (size_t)p * g.B + 1);
-            const size_t off = (srow + slot) * halfB;
-            float4 x[T];
-#pragma unroll
-            for (int t = 0; t < T; ++t) x[t] = ldg_stream(fp[t] + off);
-#pragma unroll
-            for (int t = 0; t < T; ++t) {
-                cmac2(aL[t], x[t], h0.x, h0.y, h1.x, h1.y);
-                cmac2(aR[t], x[t], h0.z, h0.w, h1.z, h1.w);
-            }
-            slot = (slot + 1 == g.P) ? 0 : slot + 1;   // modulus is partitionCount, not a power of two (Q4)
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < T; ++t) {
-        if (s0 + t <= last) {
-            acc[((size_t)(s0 + t) * 2 + 0) * halfB + jp] = aL[t];
-            acc[((size_t)(s0 + t) * 2 + 1) * halfB + jp] = aR[t];
-        }
-    }
-}
-
-cudaError_t launch_fdl_cmac(const BlockGeom &g, const float2 *fdl, const float4 *bank, float2 *acc, int tile, cudaStream_t st)
-{
-    const int halfB = g.B >> 1;
-    const int chunks = (halfB + kMacThreads - 1) / kMacThreads;
-    const int tiles = (g.n_streams + tile - 1) / tile;
-    const int grid = tiles * chunks;
-    if (grid <= 0) return cudaSuccess;
-    const float4 *f4 = reinterpret_cast<const float4 *>(fdl);
-    float4 *a4 = reinterpret_cast<float4 *>(acc);
-    switch (tile) {
-    case 1: k_fdl_cmac<1><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
-    case 2: k_fdl_cmac<2><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
-    case 4: k_fdl_cmac<4><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
-    case 8: k_fdl_cmac<8><<<grid, kMacThreads, 0, st>>>(g, f4, bank, a4); break;
-    default: return cudaErrorInvalidValue;
-    }
-    return cudaGetLastError();
-}
-
-// ------------------------------------------------------------------------------------------------
 // K6  resample (vDSP_vramp + vDSP_vgenp semantics).  Bit-exact with the oracle:
 // explicit round-to-nearest mul/add so nvcc cannot contract them into FMAs.
 // ------------------------------------------------------------------------------------------------

@@ -22,3 +22,5 @@ run fused1 AW_FUSED_TILE=1
 run split_mac2 AW_FUSED_TILE=0 AW_MAC_TILE=2
 run split_mac4 AW_FUSED_TILE=0 AW_MAC_TILE=4
 run auto AW_DUMMY=1
+run fused4_nostagger AW_FUSED_TILE=4 AW_FUSED_STAGGER=0
+run fused2_nostagger AW_FUSED_TILE=2 AW_FUSED_STAGGER=0
