@@ -37,7 +37,17 @@ __device__ __forceinline__ void smem_store(float2 *buf, const float2 (&v)[RegFft
     for (int e = 0; e < RegFft<LOG2M>::E; ++e) buf[pad16(RegFft<LOG2M>::template store_index<P>(t, e))] = v[e];
 }
 
-// Passes [P, LAST] entirely in shared memory (in place); every thread of the CTA must call it.
+// Barrier between the phases of a pass.  A transform is computed by G consecutive threads; when G <= 32 they all sit in
+// one warp, so a warp-level barrier (plus its memory ordering) is enough and the warps of a CTA run their transforms
+// independently of each other — the loads of one warp overlap the butterflies of another.
+template <int LOG2M>
+__device__ __forceinline__ void group_sync()
+{
+    if constexpr (RegFft<LOG2M>::G <= 32) __syncwarp();
+    else __syncthreads();
+}
+
+// Passes [P, LAST] entirely in shared memory (in place); every thread of the transform's group must call it.
 template <int LOG2M, int P, int LAST>
 struct SmemPasses {
     __device__ __forceinline__ static void run(float2 *buf, const float2 *tw, int t)
@@ -45,10 +55,10 @@ struct SmemPasses {
         if constexpr (P <= LAST) {
             float2 v[RegFft<LOG2M>::E];
             smem_load<LOG2M, P>(buf, v, t);
-            __syncthreads();
+            group_sync<LOG2M>();
             RegFft<LOG2M>::template compute<P>(v, tw, t);
             smem_store<LOG2M, P>(buf, v, t);
-            __syncthreads();
+            group_sync<LOG2M>();
             SmemPasses<LOG2M, P + 1, LAST>::run(buf, tw, t);
         }
     }
@@ -69,7 +79,7 @@ __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int
         F::template compute<0>(v, tw, t);
         smem_store<LOG2M, 0>(buf, v, t);
     }
-    __syncthreads();
+    group_sync<LOG2M>();
     SmemPasses<LOG2M, 1, F::PASSES - 1>::run(buf, tw, t);
     if (active) {
         for (int k = t; k <= M / 2; k += F::G) {
@@ -89,7 +99,7 @@ __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int
             }
         }
     }
-    __syncthreads();
+    group_sync<LOG2M>();
 }
 
 // Inverse real FFT: the padded buffer holds the packed spectrum acc[0..M) (acc[0].x = DC) and ny the Nyquist value;
@@ -116,7 +126,7 @@ __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float
             if (j != k) buf[pad16(j)] = make_float2(er + ti, -(-ei + tr));
         }
     }
-    __syncthreads();
+    group_sync<LOG2M>();
     SmemPasses<LOG2M, 0, F::PASSES - 2>::run(buf, tw, t);
     {
         constexpr int P = F::PASSES - 1;
@@ -131,7 +141,7 @@ __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float
             }
         }
     }
-    __syncthreads();
+    group_sync<LOG2M>();
 }
 
 __device__ __forceinline__ float group_sum(float v, int width)   // deterministic butterfly sum over `width` (<= 32) lanes
@@ -327,6 +337,142 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const Irff
 }
 
 // ------------------------------------------------------------------------------------------------
+// FDL multiply-accumulate phase shared by KF (fused) and K3 (stand-alone).
+// One thread owns one bin pair (two adjacent complex bins) of T streams.  The FDL rows are streamed with
+// cp.async (LDGSTS, 16 B per copy, L1 bypass) into a PRIVATE shared-memory ring: every thread consumes only
+// the bytes it copied itself, so the pipeline needs no barrier at all — cp.async.wait_group is the only
+// synchronisation — and the number of bytes in flight (STAGES-1 iterations x T x 16 B per thread) no longer
+// costs registers.  Filter values (both ears of both bins = 2 x float4) are prefetched one iteration ahead
+// in registers and reused for the T streams of the tile.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void cmac2f(float4 &acc, const float4 x, const float hr0, const float hi0, const float hr1, const float hi1)
+{
+    acc.x = fmaf(x.x, hr0, acc.x); acc.x = fmaf(-x.y, hi0, acc.x);
+    acc.y = fmaf(x.x, hi0, acc.y); acc.y = fmaf(x.y, hr0, acc.y);
+    acc.z = fmaf(x.z, hr1, acc.z); acc.z = fmaf(-x.w, hi1, acc.z);
+    acc.w = fmaf(x.z, hi1, acc.w); acc.w = fmaf(x.w, hr1, acc.w);
+}
+
+constexpr int kMacStages = 3;
+
+// ring: kMacStages * T * THREADS float4.  fp[u]: FDL base of stream u at this thread's bin pair (float4 units);
+// bank_jp: bank + 2*jp.  Accumulates partitions p in [p0, p1) of every speaker into aL/aR (left/right ear, 2 bins each).
+template <int T, int THREADS>
+__device__ __forceinline__ void mac_phase(const BlockGeom &g, const float4 *const (&fp)[T], const float4 *bank_jp, float4 *ring,
+                                          float4 (&aL)[T], float4 (&aR)[T], int p0, int p1)
+{
+    const int tid = threadIdx.x;
+    const int halfB = g.B >> 1;
+    const int np = p1 - p0;
+    const int total = g.S * np;
+    if (total <= 0) return;
+    int slot0 = g.head + p0;                          // ring slot of partition p0 (modulus is partitionCount, Q4)
+    if (slot0 >= g.P) slot0 -= g.P;
+    float4 *my = ring + tid;
+    // issue state (runs kMacStages-1 iterations ahead of the consume state)
+    int is = 0, ip = 0, islot = slot0, istage = 0;
+    auto issue = [&]() {
+        if (is < g.S) {
+            const size_t off = ((size_t)is * g.P_cap + islot) * halfB;
+#pragma unroll
+            for (int u = 0; u < T; ++u) cp_async16(my + (istage * T + u) * THREADS, fp[u] + off);
+            if (++ip == np) { ip = 0; ++is; islot = slot0; }
+            else islot = (islot + 1 == g.P) ? 0 : islot + 1;
+            istage = (istage + 1 == kMacStages) ? 0 : istage + 1;
+        }
+        cp_async_commit();   // always commit so the group count stays in step with the iteration count
+    };
+#pragma unroll
+    for (int k = 0; k < kMacStages - 1; ++k) issue();
+    // filter walk: (s*P + p) * B float4; consecutive p are contiguous, a speaker change skips the partitions outside [p0, p1)
+    const float4 *bk = bank_jp + (size_t)p0 * g.B;
+    const size_t skip = (size_t)(g.P - np) * g.B;
+    float4 h0 = __ldg(bk), h1 = __ldg(bk + 1);
+    int cstage = 0, cp = 0;
+    for (int it = 0; it < total; ++it) {
+        issue();
+        bk += g.B;
+        if (++cp == np) { cp = 0; bk += skip; }
+        float4 n0 = h0, n1 = h1;
+        if (it + 1 < total) { n0 = __ldg(bk); n1 = __ldg(bk + 1); }
+        cp_async_wait<kMacStages - 1>();
+#pragma unroll
+        for (int u = 0; u < T; ++u) {
+            const float4 x = my[(cstage * T + u) * THREADS];
+            cmac2f(aL[u], x, h0.x, h0.y, h1.x, h1.y);
+            cmac2f(aR[u], x, h0.z, h0.w, h1.z, h1.w);
+        }
+        h0 = n0; h1 = n1;
+        cstage = (cstage + 1 == kMacStages) ? 0 : cstage + 1;
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3  fdl_cmac (stand-alone): acc[stream][ear][bin] = sum_{s,p} FDL[stream][s][(head+p)%P][bin] * bank[s][p][bin].ear
+// (ConvolutionEngine.swift:270-350 summed over speakers as RealtimeAudioProcessor.swift:146-163 does in the time
+// domain).  Used when the fused kernel does not apply (B < 64 or B > 512).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMacThreads = 128;
+
+template <int T>
+__global__ void __launch_bounds__(kMacThreads) k_fdl_cmac(const BlockGeom g, const float4 *__restrict__ fdl,
+                                                           const float4 *__restrict__ bank, float4 *__restrict__ acc)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int halfB = g.B >> 1;
+    const int chunks = (halfB + kMacThreads - 1) / kMacThreads;
+    const int tile = blockIdx.x / chunks, chunk = blockIdx.x - tile * chunks;
+    const int jp = chunk * kMacThreads + threadIdx.x;
+    if (jp >= halfB) return;   // no barrier below: the cp.async ring is private to each thread
+    const int s0 = g.first_stream + tile * T;
+    const int last = g.first_stream + g.n_streams - 1;
+    const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+    const float4 *fp[T];
+#pragma unroll
+    for (int u = 0; u < T; ++u) fp[u] = fdl + (size_t)min(s0 + u, last) * stream_stride + jp;
+    float4 aL[T], aR[T];
+#pragma unroll
+    for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
+    mac_phase<T, kMacThreads>(g, fp, bank + 2 * jp, reinterpret_cast<float4 *>(smem_raw), aL, aR, 0, g.P);
+#pragma unroll
+    for (int u = 0; u < T; ++u) {
+        if (s0 + u <= last) {
+            acc[((size_t)(s0 + u) * 2 + 0) * halfB + jp] = aL[u];
+            acc[((size_t)(s0 + u) * 2 + 1) * halfB + jp] = aR[u];
+        }
+    }
+}
+
+cudaError_t launch_fdl_cmac(const BlockGeom &g, const float2 *fdl, const float4 *bank, float2 *acc, int tile, cudaStream_t st)
+{
+    const int halfB = g.B >> 1;
+    const int chunks = (halfB + kMacThreads - 1) / kMacThreads;
+    const int tiles = (g.n_streams + tile - 1) / tile;
+    const int grid = tiles * chunks;
+    if (grid <= 0) return cudaSuccess;
+    const float4 *f4 = reinterpret_cast<const float4 *>(fdl);
+    float4 *a4 = reinterpret_cast<float4 *>(acc);
+    const size_t smem = (size_t)kMacStages * tile * kMacThreads * sizeof(float4);
+    switch (tile) {
+    case 1: k_fdl_cmac<1><<<grid, kMacThreads, smem, st>>>(g, f4, bank, a4); break;
+    case 2: k_fdl_cmac<2><<<grid, kMacThreads, smem, st>>>(g, f4, bank, a4); break;
+    case 4: k_fdl_cmac<4><<<grid, kMacThreads, smem, st>>>(g, f4, bank, a4); break;
+    case 8: k_fdl_cmac<8><<<grid, kMacThreads, smem, st>>>(g, f4, bank, a4); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
 // KF  fused block kernel: K2 + K3 + K4 for T streams per CTA
 // ------------------------------------------------------------------------------------------------
 struct FusedArgs {
@@ -341,28 +487,15 @@ struct FusedArgs {
     const float2 *tw;
 };
 
-__device__ __forceinline__ float4 ldg_stream4(const float4 *p)
-{
-    float4 r;   // FDL history: read exactly once per block, keep it out of L1
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
-    return r;
-}
-
-__device__ __forceinline__ void cmac2f(float4 &acc, const float4 x, const float hr0, const float hi0, const float hr1, const float hi1)
-{
-    acc.x = fmaf(x.x, hr0, acc.x); acc.x = fmaf(-x.y, hi0, acc.x);
-    acc.y = fmaf(x.x, hi0, acc.y); acc.y = fmaf(x.y, hr0, acc.y);
-    acc.z = fmaf(x.z, hr1, acc.z); acc.z = fmaf(-x.w, hi1, acc.z);
-    acc.w = fmaf(x.z, hi1, acc.w); acc.w = fmaf(x.w, hr1, acc.w);
-}
-
 template <int LOG2M> struct FusedGeo {
     static constexpr int M = 1 << LOG2M;
     static constexpr int THREADS = M / 2;                // one bin pair per thread in the MAC phase
     static constexpr int G = RegFft<LOG2M>::G;
     static constexpr int NF = THREADS / G;               // = 8
     static constexpr int PS = PaddedSize<LOG2M>::value;
-    static constexpr size_t smem = (size_t)(M + NF * PS) * sizeof(float2) + (size_t)THREADS * sizeof(float);
+    static constexpr size_t fft_bytes = (size_t)NF * PS * sizeof(float2) + (size_t)THREADS * sizeof(float);
+    template <int T> static constexpr size_t ring_bytes() { return (size_t)kMacStages * T * THREADS * sizeof(float4); }
+    template <int T> static constexpr size_t smem() { return (size_t)M * sizeof(float2) + (fft_bytes > ring_bytes<T>() ? fft_bytes : ring_bytes<T>()); }
 };
 
 template <int LOG2M, int T, int MINB>
@@ -406,8 +539,9 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
             [&](int k, float2 x) { dst[k] = x; },
             [&](float ny) { *dst_ny = ny; });
     }
-    // the head slot written above is re-read below by other threads of this CTA: the barrier that ends
-    // forward_frame orders those global accesses within the block.
+    // the head slot written above is re-read below by other threads of this CTA: make the global writes visible
+    __threadfence_block();
+    __syncthreads();
 
     // ---- phase B: FDL multiply-accumulate over speakers and partitions, accumulators in registers ------------
     const int jp = tid;   // bins 2*jp, 2*jp+1
@@ -419,35 +553,8 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
     float4 aL[T], aR[T];
 #pragma unroll
     for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
-    for (int s = 0; s < g.S; ++s) {
-        const float4 *bk = a.bank + (size_t)s * g.P * M + 2 * jp;
-        const size_t srow = (size_t)s * g.P_cap;
-        {   // p = 0: the slot this CTA has just written (coherent loads)
-            const float4 h0 = __ldg(bk), h1 = __ldg(bk + 1);
-            const size_t off = (srow + g.head) * halfB;
-#pragma unroll
-            for (int u = 0; u < T; ++u) {
-                const float4 x = *(fp[u] + off);
-                cmac2f(aL[u], x, h0.x, h0.y, h1.x, h1.y);
-                cmac2f(aR[u], x, h0.z, h0.w, h1.z, h1.w);
-            }
-        }
-        int slot = g.head + 1 == g.P ? 0 : g.head + 1;
-#pragma unroll 2
-        for (int p = 1; p < g.P; ++p) {
-            const float4 h0 = __ldg(bk + (size_t)p * M), h1 = __ldg(bk + (size_t)p * M + 1);
-            const size_t off = (srow + slot) * halfB;
-            float4 x[T];
-#pragma unroll
-            for (int u = 0; u < T; ++u) x[u] = ldg_stream4(fp[u] + off);
-#pragma unroll
-            for (int u = 0; u < T; ++u) {
-                cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
-                cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
-            }
-            slot = (slot + 1 == g.P) ? 0 : slot + 1;   // modulus is partitionCount, not a power of two (Q4)
-        }
-    }
+    mac_phase<T, THREADS>(g, fp, a.bank + 2 * jp, reinterpret_cast<float4 *>(bufs), aL, aR, 0, g.P);
+    __syncthreads();   // the ring aliases the FFT buffers
 
     // ---- phase C: accumulators -> shared, Nyquist sums, inverse FFT, overlap-save discard, output -------------
 #pragma unroll
@@ -523,7 +630,7 @@ namespace {
 template <int LOG2M, int T, int MINB>
 cudaError_t launch_fused_t(const FusedArgs &a, int tiles, cudaStream_t st)
 {
-    k_fused<LOG2M, T, MINB><<<tiles, FusedGeo<LOG2M>::THREADS, FusedGeo<LOG2M>::smem, st>>>(a);
+    k_fused<LOG2M, T, MINB><<<tiles, FusedGeo<LOG2M>::THREADS, FusedGeo<LOG2M>::template smem<T>(), st>>>(a);
     return cudaGetLastError();
 }
 
@@ -550,7 +657,7 @@ template <int LOG2M, int T, int MINB>
 int fused_blocks_per_sm()
 {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<LOG2M, T, MINB>, FusedGeo<LOG2M>::THREADS, FusedGeo<LOG2M>::smem) != cudaSuccess) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fused<LOG2M, T, MINB>, FusedGeo<LOG2M>::THREADS, FusedGeo<LOG2M>::template smem<T>()) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
