@@ -181,3 +181,22 @@ def test_create_without_cuda_fails_loudly_instead_of_falling_back():
     assert e.value.status == 2   # AW_ERR_CUDA
     with pytest.raises(aw.AirwaveError):
         aw.HRIRBank(np.ones((2, 8), np.float32), 48000.0, 48000.0, [0], [1], 8)
+
+
+def test_cpp_mirror_header_compiles_and_links_against_the_abi(tmp_path):
+    """include/airwave.hpp (C++ mirror of ConvolutionEngine / RealtimeAudioProcessor) type-checks against the C ABI."""
+    exe = tmp_path / "hpp_check"
+    lib_dir = os.path.dirname(aw.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-o", str(exe), os.path.join(ROOT, "tests", "cpu", "hpp_compile_check.cpp"),
+                    "-L", lib_dir, "-lairwave_cuda", f"-Wl,-rpath,{lib_dir}"], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_swift_shim_and_module_map_are_shipped():
+    mm = open(os.path.join(ROOT, "include", "module.modulemap")).read()
+    assert "module CAirwaveCUDA" in mm and "airwave_cuda.h" in mm
+    swift = open(os.path.join(ROOT, "airwave_b200", "swift", "AirwaveCUDA.swift")).read()
+    for name in ("class ConvolutionEngine", "class RealtimeAudioProcessor", "protocol StereoAudioProcessing", "import CAirwaveCUDA"):
+        assert name in swift
+    used = set(__import__("re").findall(r"\b(aw_[a-z0-9_]+)\(", swift)) - {"aw_engine_config"}   # struct initialiser, not a call
+    assert used and used <= set(aw.declared_symbols())
