@@ -130,6 +130,9 @@ struct aw_engine {
     int macTile = 0;
     int fusedTile = 0;             // 0 = split path (K2, K3, K4), else streams per CTA of the fused kernel
     int numSMs = 148;
+    bool persistent = false;       // use the persistent warp-specialised kernel KP instead of KF
+    int persistentCtas = 0;        // CTAs of KP (default: one per SM)
+    int persistentDebug = 0;       // timing experiments only (AW_PERSISTENT_DEBUG)
     const float2 *d_tw = nullptr;
     float2 *d_fdl = nullptr;
     float *d_fdl_ny = nullptr, *d_overlap = nullptr, *d_pending = nullptr, *d_fifo = nullptr;
@@ -412,7 +415,11 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
         cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
         if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
-        if (e->fusedTile > 0) {
+        if (e->fusedTile > 0 && e->persistent && persistent_supported(e->log2m, b->P)) {
+            AW_LAUNCH(e, launch_persistent(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
+                                           e->d_tw, e->persistentCtas, e->persistentDebug, e->stream));
+            if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
+        } else if (e->fusedTile > 0) {
             // K2 + K3 + K4 in one kernel; events 0..1 bracket it, 1..3 collapse to zero-length intervals
             AW_LAUNCH(e, launch_fused(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
                                       e->d_tw, e->fusedTile, e->stream));
@@ -828,6 +835,14 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
     }
     // fused-kernel plan: the CTA owns whole streams, so the grid is n/T CTAs; prefer the largest tile (most filter
     // reuse) that still fits in ONE wave of resident CTAs, else the tile with the least wave-quantisation loss.
+    {
+        const char *p_env = getenv("AW_PERSISTENT");
+        e->persistent = !(p_env && atoi(p_env) == 0);   // KP is the default; AW_PERSISTENT=0 selects KF
+        const char *c_env = getenv("AW_PERSISTENT_CTAS");
+        e->persistentCtas = c_env && atoi(c_env) > 0 ? atoi(c_env) : e->numSMs;
+        const char *d_env = getenv("AW_PERSISTENT_DEBUG");
+        e->persistentDebug = d_env ? atoi(d_env) : 0;
+    }
     e->fusedTile = 0;
     const char *fused_env = getenv("AW_FUSED_TILE");   // 0 forces the split path, 1/2/4 force a tile
     if (fused_supported(e->log2m) && !(fused_env && atoi(fused_env) == 0)) {

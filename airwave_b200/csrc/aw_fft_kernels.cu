@@ -67,18 +67,16 @@ struct SmemPasses {
 // Forward real FFT of one frame.  `load(i)` returns z[i] = x[2i] + i*x[2i+1] of the frame (i < M); on return the
 // padded buffer holds Z and (after the trailing barrier) `emit(k, X)` has been called by the owning threads for
 // k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
-template <int LOG2M, class Load, class Emit, class EmitNy>
-__device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int t, bool active, Load load, Emit emit, EmitNy emit_ny)
+// Body of the forward real FFT of one frame whose pass-0 operands are already in registers (v[e] = z[load_index<0>(t, e)]):
+// lets a caller fetch the next frame from global memory while this one is being transformed.
+template <int LOG2M, class Emit, class EmitNy>
+__device__ __forceinline__ void forward_frame_regs(float2 *buf, const float2 *tw, int t, bool active, float2 (&v)[RegFft<LOG2M>::E],
+                                                   Emit emit, EmitNy emit_ny)
 {
     using F = RegFft<LOG2M>;
     constexpr int M = F::M;
-    {
-        float2 v[F::E];
-#pragma unroll
-        for (int e = 0; e < F::E; ++e) v[e] = active ? load(F::template load_index<0>(t, e), e) : make_float2(0.f, 0.f);
-        F::template compute<0>(v, tw, t);
-        smem_store<LOG2M, 0>(buf, v, t);
-    }
+    F::template compute<0>(v, tw, t);
+    smem_store<LOG2M, 0>(buf, v, t);
     group_sync<LOG2M>();
     SmemPasses<LOG2M, 1, F::PASSES - 1>::run(buf, tw, t);
     if (active) {
@@ -100,6 +98,18 @@ __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int
         }
     }
     group_sync<LOG2M>();
+}
+
+// Forward real FFT of one frame.  `load(i)` returns z[i] = x[2i] + i*x[2i+1] of the frame (i < M); `emit(k, X)` is called
+// by the owning threads for k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
+template <int LOG2M, class Load, class Emit, class EmitNy>
+__device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int t, bool active, Load load, Emit emit, EmitNy emit_ny)
+{
+    using F = RegFft<LOG2M>;
+    float2 v[F::E];
+#pragma unroll
+    for (int e = 0; e < F::E; ++e) v[e] = active ? load(F::template load_index<0>(t, e), e) : make_float2(0.f, 0.f);
+    forward_frame_regs<LOG2M>(buf, tw, t, active, v, emit, emit_ny);
 }
 
 // Inverse real FFT: the padded buffer holds the packed spectrum acc[0..M) (acc[0].x = DC) and ny the Nyquist value;
@@ -160,11 +170,22 @@ __device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fd
     float sum = 0.f;
     if (active) {
         const int terms = g.S * g.P;
-        for (int i = t; i < terms; i += G) {
-            const int s = i / g.P, p = i - s * g.P;
-            int slot = g.head + p;
-            if (slot >= g.P) slot -= g.P;
-            sum = fmaf(fdl_ny[((size_t)stream * g.Se + s) * g.P_cap + slot], bank_ny[(size_t)i * 2 + ear], sum);
+        for (int i0 = t; i0 < terms; i0 += 8 * G) {     // 8 independent load pairs in flight per thread
+            float xa[8], ha[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int i = i0 + k * G;
+                xa[k] = 0.f; ha[k] = 0.f;
+                if (i < terms) {
+                    const int s = i / g.P, p = i - s * g.P;
+                    int slot = g.head + p;
+                    if (slot >= g.P) slot -= g.P;
+                    xa[k] = fdl_ny[((size_t)stream * g.Se + s) * g.P_cap + slot];
+                    ha[k] = bank_ny[(size_t)i * 2 + ear];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) sum = fmaf(xa[k], ha[k], sum);
         }
     }
     if constexpr (G <= 32) {
@@ -574,6 +595,307 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
         float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
         inverse_frame<LOG2M>(bufs + (size_t)f * FG::PS, ny, tw, t, active,
                              [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// KP  persistent warp-specialised block kernel (64 <= B <= 512): one CTA per SM walks over tiles of 4 streams.
+//
+//   warp 0            producer: one elected thread streams the FDL *history* rows (partitions p >= 1) of tile after
+//                     tile, plus the matching filter rows, into a deep shared-memory ring with TMA-class bulk copies
+//                     (cp.async.bulk ... mbarrier::complete_tx).  It never waits for anything but a free ring stage, so
+//                     HBM stays busy across tile boundaries and while other warps transform.
+//   MAC warps (B/2 threads)   one bin pair of the 4 streams per thread; consume ring stages (full/empty mbarriers), then
+//                     add the head partition (p = 0, just written by the FFT warps, read with plain loads).
+//   FFT warps (B/2 threads)   while the MAC warps stream the history of tile i they run the inverse transforms of tile i-1
+//                     (accumulators handed over through shared memory) and the forward transforms of tile i.
+//
+// The two latency-bound phases of KF (input FFT, inverse FFT) thereby run in the shadow of the bandwidth-bound phase.
+// Named barriers: HEAD_READY (FFT -> MAC), ACC_READY (MAC -> FFT), ACC_FREE (FFT -> MAC).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <int LOG2M> struct PersistGeo {
+    static constexpr int M = 1 << LOG2M, halfB = M / 2, T = 4;
+    static constexpr int G = RegFft<LOG2M>::G;
+    static constexpr int PRODUCERS = 4;                                     // producer warps, one issuing lane each
+    static constexpr int MAC_GROUPS = 2, TG = T / MAC_GROUPS;               // two groups of MAC warps, 2 streams each
+    static constexpr int FFT_GROUPS = 1, NFT = 8 * FFT_GROUPS;             // transforms the FFT warps run side by side
+    static constexpr int MAC_THREADS = MAC_GROUPS * halfB, FFT_THREADS = FFT_GROUPS * halfB;
+    static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
+    static constexpr int PS = PaddedSize<LOG2M>::value;
+    static constexpr size_t stage_bytes = (size_t)T * halfB * sizeof(float4) + (size_t)M * sizeof(float4);   // T FDL rows + one filter row
+    static constexpr size_t fixed_bytes = (size_t)M * sizeof(float2)               // twiddles
+                                          + (size_t)(NFT + 8) * PS * sizeof(float2) // FFT buffers + accumulator hand-over buffers
+                                          + 512;                                   // mbarriers (2 x STAGES x 8 B)
+    static constexpr int max_stages = (int)((220 * 1024 - fixed_bytes) / stage_bytes);
+    static constexpr int STAGES = max_stages > 24 ? 24 : max_stages;
+    static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
+};
+
+struct PersistArgs {
+    BlockGeom g;
+    StridedIn cur, prev;
+    float *overlap_save;
+    float2 *fdl;
+    float *fdl_ny;
+    const float4 *bank;
+    const float *bank_ny;
+    StridedOut out;
+    const float2 *tw;
+    int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms
+};
+
+template <int LOG2M>
+__global__ void __launch_bounds__(PersistGeo<LOG2M>::THREADS, 1) k_persistent(const PersistArgs a)
+{
+    using PG = PersistGeo<LOG2M>;
+    constexpr int M = PG::M, halfB = PG::halfB, T = PG::T, TG = PG::TG, G = PG::G, STAGES = PG::STAGES, PS = PG::PS;
+    constexpr int BAR_HEAD_READY = 1, BAR_ACC_READY = 2, BAR_ACC_FREE = 3, PAIR = PG::MAC_THREADS + PG::FFT_THREADS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *ring = reinterpret_cast<float4 *>(smem_raw);                                   // STAGES x (T*halfB + M) float4
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw + (size_t)STAGES * PG::stage_bytes);
+    float2 *fftbuf = tw + M;
+    float2 *accbuf = fftbuf + (size_t)PG::NFT * PS;
+    uint64_t *full = reinterpret_cast<uint64_t *>(accbuf + (size_t)8 * PS);
+    uint64_t *empty = full + STAGES;
+    const BlockGeom &g = a.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (g.n_streams + T - 1) / T;
+    const int last = g.first_stream + g.n_streams - 1;
+    const int old_iters = g.S * (g.P - 1);
+    constexpr int stage_f4 = T * halfB + M;
+
+    for (int k = tid; k < M; k += PG::THREADS) tw[k] = a.tw[k];
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PG::MAC_THREADS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp < PG::PRODUCERS) {
+        // ===== producers: warp w issues the iterations k = w, w + PRODUCERS, ... of this CTA's iteration sequence =====
+        if (lane == 0 && old_iters > 0) {
+            const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+            const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
+            const int pm1 = g.P - 1;
+            long long k = warp;                       // global iteration index over (tile_local, s, p-1)
+            int tile = blockIdx.x;
+            int rem = warp;                           // iteration within the tile
+            while (rem >= old_iters) { rem -= old_iters; tile += gridDim.x; }
+            while (tile < n_tiles) {
+                const int s = rem / pm1, p = 1 + (rem - s * pm1);
+                int slot = g.head + p;
+                if (slot >= g.P) slot -= g.P;         // modulus is partitionCount (Q4)
+                const int stage = (int)(k % STAGES);
+                const unsigned phase = (unsigned)((k / STAGES) & 1);
+                const int s0 = g.first_stream + tile * T;
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_expect_tx(&full[stage], (unsigned)PG::stage_bytes);
+                float4 *dst = ring + (size_t)stage * stage_f4;
+#pragma unroll
+                for (int u = 0; u < T; ++u)
+                    bulk_g2s(dst + u * halfB, fdl4 + (size_t)min(s0 + u, last) * stream_stride + ((size_t)s * g.P_cap + slot) * halfB,
+                             (unsigned)(halfB * sizeof(float4)), &full[stage]);
+                bulk_g2s(dst + T * halfB, a.bank + ((size_t)s * g.P + p) * M, (unsigned)(M * sizeof(float4)), &full[stage]);
+                k += PG::PRODUCERS;
+                rem += PG::PRODUCERS;
+                while (rem >= old_iters) { rem -= old_iters; tile += gridDim.x; }
+            }
+        }
+    } else if (warp < PG::PRODUCERS + PG::MAC_THREADS / 32) {
+        // ===== MAC warps: group gi owns streams 2*gi, 2*gi+1 of the tile; one bin pair per thread =====
+        const int mt = tid - 32 * PG::PRODUCERS;
+        const int gi = mt / halfB, jp = mt - gi * halfB;   // bins 2*jp, 2*jp+1
+        int stage = 0;
+        unsigned phase = 0;
+        const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+        const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
+        int local = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            const int s0 = g.first_stream + tile * T + gi * TG;
+            float4 aL[TG], aR[TG];
+#pragma unroll
+            for (int u = 0; u < TG; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
+            for (int it = 0; it < old_iters; ++it) {
+                mbar_wait(&full[stage], phase);
+                const float4 *src = ring + (size_t)stage * stage_f4;
+                const float4 h0 = src[T * halfB + 2 * jp], h1 = src[T * halfB + 2 * jp + 1];
+                float4 x[TG];
+#pragma unroll
+                for (int u = 0; u < TG; ++u) x[u] = src[(gi * TG + u) * halfB + jp];
+#pragma unroll
+                for (int u = 0; u < TG; ++u) {
+                    cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
+                    cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            }
+            // head partition (p = 0): written by this CTA's FFT warps for this very block
+            named_sync(BAR_HEAD_READY, PAIR);
+            for (int s = 0; s < g.S; ++s) {
+                const float4 h0 = __ldg(a.bank + (size_t)s * g.P * M + 2 * jp), h1 = __ldg(a.bank + (size_t)s * g.P * M + 2 * jp + 1);
+                const size_t off = ((size_t)s * g.P_cap + g.head) * halfB + jp;
+                float4 x[TG];
+#pragma unroll
+                for (int u = 0; u < TG; ++u) x[u] = *(fdl4 + (size_t)min(s0 + u, last) * stream_stride + off);
+#pragma unroll
+                for (int u = 0; u < TG; ++u) {
+                    cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
+                    cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
+                }
+            }
+            if (local > 0) named_sync(BAR_ACC_FREE, PAIR);   // the FFT warps are done with the previous accumulators
+#pragma unroll
+            for (int u = 0; u < TG; ++u) {
+                float2 *bl = accbuf + (size_t)(2 * (gi * TG + u)) * PS, *br = bl + PS;
+                bl[pad16(2 * jp)] = make_float2(aL[u].x, aL[u].y);
+                bl[pad16(2 * jp + 1)] = make_float2(aL[u].z, aL[u].w);
+                br[pad16(2 * jp)] = make_float2(aR[u].x, aR[u].y);
+                br[pad16(2 * jp + 1)] = make_float2(aR[u].z, aR[u].w);
+            }
+            __threadfence_block();
+            named_arrive(BAR_ACC_READY, PAIR);
+        }
+    } else {
+        // ===== FFT warps =====
+        const int ft = tid - 32 * PG::PRODUCERS - PG::MAC_THREADS;
+        const int f = ft / G, t = ft % G;
+        auto inverse_tile = [&](int tile) {
+            const int s0 = g.first_stream + tile * T;
+            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
+            if (f >= 8) return;                 // 2*T = 8 inverse transforms; transforms never share a warp with f < 8 (8*G >= 32)
+            const int ls = f >> 1, ear = f & 1;
+            const bool active = ls < nvalid;
+            const int stream = s0 + (active ? ls : 0);
+            const float ny = nyquist_sum<G>(g, a.fdl_ny, a.bank_ny, stream, ear, active, t, nullptr);
+            float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
+            inverse_frame<LOG2M>(accbuf + (size_t)f * PS, ny, tw, t, active,
+                                 [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
+        };
+        int local = 0, prev_tile = -1;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
+            if (local > 0) {
+                named_sync(BAR_ACC_READY, PAIR);
+                if (!(a.debug & 2)) inverse_tile(prev_tile);
+                __syncwarp();
+                named_arrive(BAR_ACC_FREE, PAIR);
+            }
+            const int s0 = g.first_stream + tile * T;
+            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
+            const int nfft = T * g.S;
+            using F = RegFft<LOG2M>;
+            // round r transforms frames r*8 + f; the operands of round r+1 are fetched before round r is transformed
+            auto fetch = [&](int base, float2 (&v)[F::E], bool &active, int &stream, int &s) {
+                const int idx = base + f;
+                const int ls = idx / g.S;
+                s = idx - ls * g.S;
+                active = idx < nfft && ls < nvalid;
+                stream = s0 + (active ? ls : 0);
+                const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
+                const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
+#pragma unroll
+                for (int e = 0; e < F::E; ++e) {
+                    const int i = F::template load_index<0>(t, e);
+                    v[e] = !active ? make_float2(0.f, 0.f)
+                                   : (i < M / 2 ? *reinterpret_cast<const float2 *>(prev + 2 * i) : *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2)));
+                }
+            };
+            float2 v[F::E], vn[F::E];
+            bool active = false, active_n = false;
+            int stream = 0, sp = 0, stream_n = 0, sp_n = 0;
+            const int base0 = (a.debug & 1) ? nfft : 0;
+            if (base0 < nfft) fetch(base0, v, active, stream, sp);
+            for (int base = base0; base < nfft; base += PG::NFT) {
+                if (base + PG::NFT < nfft) fetch(base + PG::NFT, vn, active_n, stream_n, sp_n);
+                if (active && a.overlap_save) {   // inputOverlapBuffer <- current block (the same thread read these addresses as `prev`)
+                    float *ov = a.overlap_save + ((size_t)stream * g.Se + sp) * M;
+#pragma unroll
+                    for (int e = 0; e < F::E; ++e) {
+                        const int i = F::template load_index<0>(t, e);
+                        if (i >= M / 2) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v[e];
+                    }
+                }
+                const size_t row = ((size_t)stream * g.Se + sp) * g.P_cap + g.head;
+                float2 *dst = a.fdl + row * M;
+                float *dst_ny = a.fdl_ny + row;
+                forward_frame_regs<LOG2M>(fftbuf + (size_t)f * PS, tw, t, active, v,
+                                          [&](int k, float2 x) { dst[k] = x; }, [&](float ny) { *dst_ny = ny; });
+#pragma unroll
+                for (int e = 0; e < F::E; ++e) v[e] = vn[e];
+                active = active_n; stream = stream_n; sp = sp_n;
+            }
+            __threadfence_block();
+            named_arrive(BAR_HEAD_READY, PAIR);
+            prev_tile = tile;
+        }
+        if (prev_tile >= 0) {
+            named_sync(BAR_ACC_READY, PAIR);
+            if (!(a.debug & 2)) inverse_tile(prev_tile);
+        }
+    }
+}
+
+template <int LOG2M>
+cudaError_t launch_persistent_l(const PersistArgs &a, int ctas, cudaStream_t st)
+{
+    static bool configured = false;   // opt in to the large dynamic shared memory once per process
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(k_persistent<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistGeo<LOG2M>::smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    k_persistent<LOG2M><<<ctas, PersistGeo<LOG2M>::THREADS, PersistGeo<LOG2M>::smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+bool persistent_supported(int log2m, int P) { return log2m >= 6 && log2m <= 9 && P >= 1; }
+
+cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
+                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int num_sms, int debug,
+                              cudaStream_t st)
+{
+    if (g.n_streams <= 0) return cudaSuccess;
+    PersistArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, bank, bank_ny, out, tw, debug};
+    const int tiles = (g.n_streams + 3) / 4;
+    const int ctas = tiles < num_sms ? tiles : num_sms;
+    switch (g.log2m) {
+    case 6: return launch_persistent_l<6>(a, ctas, st);
+    case 7: return launch_persistent_l<7>(a, ctas, st);
+    case 8: return launch_persistent_l<8>(a, ctas, st);
+    case 9: return launch_persistent_l<9>(a, ctas, st);
+    default: return cudaErrorInvalidValue;
     }
 }
 

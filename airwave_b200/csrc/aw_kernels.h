@@ -79,6 +79,12 @@ int fused_blocks_per_sm(int log2m, int tile);   // resident CTAs per SM of that 
 cudaError_t launch_fused(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
                          const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, cudaStream_t st);
 
+// KP: persistent warp-specialised variant of KF (one CTA per SM, TMA bulk-copy ring, FFT warps overlapped with MAC warps).
+bool persistent_supported(int log2m, int P);
+cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
+                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int num_sms, int debug,
+                              cudaStream_t st);
+
 size_t fft_smem_bytes(int log2m);
 cudaError_t configure_kernels(int log2m);   // opt in to > 48 KB dynamic shared memory for that transform size
 
