@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
     L.aw_engine_stream.restype = vp; L.aw_engine_stream.argtypes = [vp]
     L.aw_engine_profile_begin.argtypes = [vp, C.c_int]
     L.aw_engine_plan.argtypes = [vp, ip, ip, ip]
+    L.aw_engine_kernels.argtypes = [vp, C.c_char_p, C.c_int]
     L.aw_engine_profile_end.argtypes = [vp, dp, ull]
     L.aw_host_alloc.restype = vp; L.aw_host_alloc.argtypes = [C.c_size_t]
     L.aw_host_free.argtypes = [vp]; L.aw_host_free.restype = None

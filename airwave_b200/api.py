@@ -336,17 +336,26 @@ class BinauralEngine:
     def plan(self) -> dict:
         f, m, p = C.c_int(), C.c_int(), C.c_int()
         L.check(L.lib().aw_engine_plan(self._h, C.byref(f), C.byref(m), C.byref(p)))
-        return dict(fused_tile=f.value, mac_tile=m.value, partitions_cap=p.value)
+        return dict(fused_tile=f.value, mac_tile=m.value, partitions_cap=p.value, kernels=self.kernels())
+
+    def kernels(self) -> list:
+        """Names of the kernels launched per block, in launch order (e.g. ['k_persistent<8,4>'])."""
+        buf = C.create_string_buffer(256)
+        L.check(L.lib().aw_engine_kernels(self._h, buf, 256))
+        return buf.value.decode().split(",")
 
     def profile_begin(self, max_blocks: int) -> None:
         L.check(L.lib().aw_engine_profile_begin(self._h, max_blocks))
 
     def profile_end(self) -> dict:
-        ms = (C.c_double * 3)()
-        cnt = (C.c_ulonglong * 3)()
+        """{kernel name: {ms, launches}} summed over the profiled blocks; 'k_eq' = the equalizer launches of a call."""
+        ms = (C.c_double * 4)()
+        cnt = (C.c_ulonglong * 4)()
         L.check(L.lib().aw_engine_profile_end(self._h, ms, cnt))
-        names = ["fused", "-", "-"] if self.plan()["fused_tile"] > 0 else ["input_rfft", "fdl_cmac", "irfft_out"]
-        return {n: dict(ms=ms[i], launches=cnt[i]) for i, n in enumerate(names) if n != "-"}
+        out = {n: dict(ms=ms[i], launches=cnt[i]) for i, n in enumerate(self.kernels())}
+        if cnt[3] and ms[3] > 0:
+            out["k_eq"] = dict(ms=ms[3], launches=cnt[3])
+        return out
 
     @property
     def cuda_stream(self) -> int:

@@ -12,8 +12,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libairwave_cuda.so")
-SOURCES = ["aw_api.cu", "aw_kernels.cu", "aw_fft_kernels.cu", "aw_host.cpp"]
-HEADERS = ["aw_fft.cuh", "aw_fft_reg.cuh", "aw_kernels.h", "aw_internal.h", os.path.join("..", "..", "include", "airwave_cuda.h")]
+SOURCES = ["aw_api.cu", "aw_kernels.cu", "aw_fft_kernels.cu", "aw_persistent.cu", "aw_host.cpp"]
+HEADERS = ["aw_fft.cuh", "aw_fft_reg.cuh", "aw_fft_blocks.cuh", "aw_kernels.h", "aw_internal.h", os.path.join("..", "..", "include", "airwave_cuda.h")]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-cudart", "static",

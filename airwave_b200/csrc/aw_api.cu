@@ -90,7 +90,7 @@ int get_plan(int device, int log2n, const float2 **out)
 // ---- opaque types ----------------------------------------------------------------------------------
 struct aw_bank {
     int device = 0, S = 0, B = 0, log2m = 0, P = 0, taps = 0;
-    float4 *d_bank = nullptr;   // [S][P][B] {L.re, L.im, R.re, R.im}
+    float4 *d_bank = nullptr;   // [S][P][2 planes: even bins, odd bins][B/2] {L.re, L.im, R.re, R.im}
     float *d_ny = nullptr;      // [S][P][2]
 };
 
@@ -130,7 +130,8 @@ struct aw_engine {
     int macTile = 0;
     int fusedTile = 0;             // 0 = split path (K2, K3, K4), else streams per CTA of the fused kernel
     int numSMs = 148;
-    bool persistent = false;       // use the persistent warp-specialised kernel KP instead of KF
+    bool persistent = false;       // use the persistent warp-specialised kernel KP (aw_persistent.cu) instead of KF
+    int persistentTile = 0;        // streams per tile of KP (4 or 2)
     int persistentCtas = 0;        // CTAs of KP (default: one per SM)
     int persistentDebug = 0;       // timing experiments only (AW_PERSISTENT_DEBUG)
     const float2 *d_tw = nullptr;
@@ -153,8 +154,8 @@ struct aw_engine {
     int pendingCount = 0, fifoReadIndex = 0, fifoCount = 0;
     unsigned long long launches = 0, blocks = 0, h2dBytes = 0, d2hBytes = 0;
     // optional per-kernel event timing (benchmarks only)
-    std::vector<cudaEvent_t> profEvents;
-    size_t profUsed = 0;
+    std::vector<cudaEvent_t> profEvents, profEqEvents;
+    size_t profUsed = 0, profEqUsed = 0;
     bool profOn = false;
 };
 
@@ -415,9 +416,9 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
         cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
         if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
-        if (e->fusedTile > 0 && e->persistent && persistent_supported(e->log2m, b->P)) {
+        if (e->persistent) {
             AW_LAUNCH(e, launch_persistent(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
-                                           e->d_tw, e->persistentCtas, e->persistentDebug, e->stream));
+                                           e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, e->stream));
             if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
         } else if (e->fusedTile > 0) {
             // K2 + K3 + K4 in one kernel; events 0..1 bracket it, 1..3 collapse to zero-length intervals
@@ -499,10 +500,13 @@ int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, 
         }
     }
     // equalizer after spatial (AudioEffectGraph.swift:195-210), in place on the output
+    const bool prof = e->profOn && e->profEqUsed + 2 <= e->profEqEvents.size();
+    if (prof) cudaEventRecord(e->profEqEvents[e->profEqUsed], e->stream);
     for (EqMachine &m : e->machines) {
         const int rc = eq_process_machine(e, m, out, frames);
         if (rc != AW_OK) return rc;
     }
+    if (prof) { cudaEventRecord(e->profEqEvents[e->profEqUsed + 1], e->stream); e->profEqUsed += 2; }
     return AW_OK;
 }
 
@@ -520,6 +524,7 @@ void free_engine(aw_engine *e)
         if (s.out_done) cudaEventDestroy(s.out_done);
     }
     for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : e->profEqEvents) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
     if (e->d2h) cudaStreamDestroy(e->d2h);
@@ -742,7 +747,15 @@ extern "C" int aw_bank_read(const aw_bank *bank, float *spectrum, float *nyquist
 {
     if (!bank) return set_error(AW_ERR_INVALID_ARGUMENT, "null bank");
     DeviceGuard guard(bank->device);
-    if (spectrum) AW_CUDA(cudaMemcpy(spectrum, bank->d_bank, sizeof(float4) * (size_t)bank->S * bank->P * bank->B, cudaMemcpyDeviceToHost));
+    if (spectrum) {
+        // device rows are two planes (even bins, odd bins) of B/2 float4; the host view is bin-major
+        const size_t rows = (size_t)bank->S * bank->P, B = (size_t)bank->B, half = B / 2;
+        std::vector<float4> tmp(rows * B);
+        AW_CUDA(cudaMemcpy(tmp.data(), bank->d_bank, sizeof(float4) * rows * B, cudaMemcpyDeviceToHost));
+        float4 *dst = reinterpret_cast<float4 *>(spectrum);
+        for (size_t r = 0; r < rows; ++r)
+            for (size_t k = 0; k < B; ++k) dst[r * B + k] = tmp[r * B + (k & 1) * half + (k >> 1)];
+    }
     if (nyquist) AW_CUDA(cudaMemcpy(nyquist, bank->d_ny, sizeof(float) * (size_t)bank->S * bank->P * 2, cudaMemcpyDeviceToHost));
     return AW_OK;
 }
@@ -833,19 +846,36 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         cudaDeviceProp prop;
         if (cudaGetDeviceProperties(&prop, config->device) == cudaSuccess) e->numSMs = prop.multiProcessorCount;
     }
-    // fused-kernel plan: the CTA owns whole streams, so the grid is n/T CTAs; prefer the largest tile (most filter
-    // reuse) that still fits in ONE wave of resident CTAs, else the tile with the least wave-quantisation loss.
+    // Plan.  KP (persistent, aw_persistent.cu) is the default wherever it exists (64 <= B <= 2048); AW_PERSISTENT=0 selects
+    // the single-wave fused kernel KF (64 <= B <= 512) and AW_FUSED_TILE=0 the split kernels K2/K3/K4 for comparisons.
+    // None of these choices changes a stream's arithmetic with the number of streams: the tile size only sets how many
+    // streams share one pass over the filter rows.
+    e->fusedTile = 0;
+    const char *fused_env = getenv("AW_FUSED_TILE");   // 0 forces the split path, 1/2/4 force a KF tile
+    const bool force_split = fused_env && atoi(fused_env) == 0;
     {
         const char *p_env = getenv("AW_PERSISTENT");
-        e->persistent = !(p_env && atoi(p_env) == 0);   // KP is the default; AW_PERSISTENT=0 selects KF
+        const int mask = persistent_tiles(e->log2m);
+        e->persistent = mask != 0 && !force_split && !(p_env && atoi(p_env) == 0);
         const char *c_env = getenv("AW_PERSISTENT_CTAS");
         e->persistentCtas = c_env && atoi(c_env) > 0 ? atoi(c_env) : e->numSMs;
         const char *d_env = getenv("AW_PERSISTENT_DEBUG");
         e->persistentDebug = d_env ? atoi(d_env) : 0;
+        if (e->persistent) {
+            // largest tile (most filter reuse) unless the smaller one loses clearly less to round quantisation
+            auto eff = [&](int T) {
+                const double tiles = (double)((e->n + T - 1) / T);
+                return (double)e->n / ((double)T * std::ceil(tiles / e->persistentCtas) * e->persistentCtas);
+            };
+            e->persistentTile = (mask & 4) ? 4 : 2;
+            if ((mask & 4) && (mask & 2) && eff(2) > 1.08 * eff(4)) e->persistentTile = 2;
+            const char *t_env = getenv("AW_PERSISTENT_TILE");
+            if (t_env && (atoi(t_env) & mask) && (atoi(t_env) == 2 || atoi(t_env) == 4)) e->persistentTile = atoi(t_env);
+        }
     }
-    e->fusedTile = 0;
-    const char *fused_env = getenv("AW_FUSED_TILE");   // 0 forces the split path, 1/2/4 force a tile
-    if (fused_supported(e->log2m) && !(fused_env && atoi(fused_env) == 0)) {
+    if (!e->persistent && fused_supported(e->log2m) && !force_split) {
+        // KF: the CTA owns whole streams, so the grid is n/T CTAs; prefer the largest tile that still fits in ONE wave of
+        // resident CTAs, else the tile with the least wave-quantisation loss.
         int forced = fused_env ? atoi(fused_env) : -1;
         if (forced == 1 || forced == 2 || forced == 4) e->fusedTile = forced;
         else {
@@ -1158,7 +1188,7 @@ extern "C" int aw_engine_counters(const aw_engine *e, unsigned long long *kernel
 extern "C" int aw_engine_plan(const aw_engine *e, int *fused_tile, int *mac_tile, int *partitions_cap)
 {
     if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
-    if (fused_tile) *fused_tile = e->fusedTile;
+    if (fused_tile) *fused_tile = e->persistent ? e->persistentTile : e->fusedTile;
     if (mac_tile) *mac_tile = e->macTile;
     if (partitions_cap) *partitions_cap = e->P_cap;
     return AW_OK;
@@ -1174,7 +1204,13 @@ extern "C" int aw_engine_profile_begin(aw_engine *e, int max_blocks)
         AW_CUDA(cudaEventCreate(&ev));
         e->profEvents.push_back(ev);
     }
+    while (e->profEqEvents.size() < (size_t)max_blocks * 2) {
+        cudaEvent_t ev;
+        AW_CUDA(cudaEventCreate(&ev));
+        e->profEqEvents.push_back(ev);
+    }
     e->profUsed = 0;
+    e->profEqUsed = 0;
     e->profOn = true;
     return AW_OK;
 }
@@ -1185,8 +1221,8 @@ extern "C" int aw_engine_profile_end(aw_engine *e, double *kernel_ms, unsigned l
     DeviceGuard guard(e->cfg.device);
     e->profOn = false;
     AW_CUDA(cudaStreamSynchronize(e->stream));
-    double ms[3] = {0, 0, 0};
-    unsigned long long cnt[3] = {0, 0, 0};
+    double ms[4] = {0, 0, 0, 0};
+    unsigned long long cnt[4] = {0, 0, 0, 0};
     for (size_t i = 0; i + 4 <= e->profUsed; i += 4) {
         for (int k = 0; k < 3; ++k) {
             float t = 0.f;
@@ -1195,11 +1231,31 @@ extern "C" int aw_engine_profile_end(aw_engine *e, double *kernel_ms, unsigned l
             ++cnt[k];
         }
     }
-    for (int k = 0; k < 3; ++k) {
+    for (size_t i = 0; i + 2 <= e->profEqUsed; i += 2) {   // slot 3: the equalizer launches of one process call
+        float t = 0.f;
+        AW_CUDA(cudaEventElapsedTime(&t, e->profEqEvents[i], e->profEqEvents[i + 1]));
+        ms[3] += t;
+        ++cnt[3];
+    }
+    for (int k = 0; k < 4; ++k) {
         if (kernel_ms) kernel_ms[k] = ms[k];
         if (kernel_launches) kernel_launches[k] = cnt[k];
     }
     e->profUsed = 0;
+    e->profEqUsed = 0;
+    return AW_OK;
+}
+
+extern "C" int aw_engine_kernels(const aw_engine *e, char *names, int capacity)
+{
+    if (!e || !names || capacity <= 0) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_kernels: bad argument");
+    const int lb = e->log2m;
+    std::string n;
+    if (e->persistent) n = "k_persistent<" + std::to_string(lb) + "," + std::to_string(e->persistentTile) + ">";
+    else if (e->fusedTile > 0) n = "k_fused<" + std::to_string(lb) + "," + std::to_string(e->fusedTile) + ">";
+    else n = "k_input_rfft<" + std::to_string(lb) + ">,k_fdl_cmac<" + std::to_string(e->macTile) + ">,k_irfft_out<" + std::to_string(lb) + ">";
+    if ((int)n.size() + 1 > capacity) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_kernels: capacity too small");
+    memcpy(names, n.c_str(), n.size() + 1);
     return AW_OK;
 }
 

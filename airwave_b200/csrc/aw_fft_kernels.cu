@@ -11,198 +11,10 @@
 // Thread organisation: a transform of M = B complex points is done by G = M/16 threads holding 16 values each;
 // a CTA runs NF transforms side by side.  In the fused kernel THREADS = B/2 (one bin pair per thread in the MAC
 // phase) which makes NF = 8 for every supported B.
-#include <stdint.h>
-
-#include "aw_fft_reg.cuh"
-#include "aw_kernels.h"
+#include "aw_fft_blocks.cuh"
 
 namespace aw {
 
-using namespace awfft;
-
-// ------------------------------------------------------------------------------------------------
-// building blocks
-// ------------------------------------------------------------------------------------------------
-template <int LOG2M, int P>
-__device__ __forceinline__ void smem_load(const float2 *buf, float2 (&v)[RegFft<LOG2M>::E], int t)
-{
-#pragma unroll
-    for (int e = 0; e < RegFft<LOG2M>::E; ++e) v[e] = buf[pad16(RegFft<LOG2M>::template load_index<P>(t, e))];
-}
-
-template <int LOG2M, int P>
-__device__ __forceinline__ void smem_store(float2 *buf, const float2 (&v)[RegFft<LOG2M>::E], int t)
-{
-#pragma unroll
-    for (int e = 0; e < RegFft<LOG2M>::E; ++e) buf[pad16(RegFft<LOG2M>::template store_index<P>(t, e))] = v[e];
-}
-
-// Barrier between the phases of a pass.  A transform is computed by G consecutive threads; when G <= 32 they all sit in
-// one warp, so a warp-level barrier (plus its memory ordering) is enough and the warps of a CTA run their transforms
-// independently of each other — the loads of one warp overlap the butterflies of another.
-template <int LOG2M>
-__device__ __forceinline__ void group_sync()
-{
-    if constexpr (RegFft<LOG2M>::G <= 32) __syncwarp();
-    else __syncthreads();
-}
-
-// Passes [P, LAST] entirely in shared memory (in place); every thread of the transform's group must call it.
-template <int LOG2M, int P, int LAST>
-struct SmemPasses {
-    __device__ __forceinline__ static void run(float2 *buf, const float2 *tw, int t)
-    {
-        if constexpr (P <= LAST) {
-            float2 v[RegFft<LOG2M>::E];
-            smem_load<LOG2M, P>(buf, v, t);
-            group_sync<LOG2M>();
-            RegFft<LOG2M>::template compute<P>(v, tw, t);
-            smem_store<LOG2M, P>(buf, v, t);
-            group_sync<LOG2M>();
-            SmemPasses<LOG2M, P + 1, LAST>::run(buf, tw, t);
-        }
-    }
-};
-
-// Forward real FFT of one frame.  `load(i)` returns z[i] = x[2i] + i*x[2i+1] of the frame (i < M); on return the
-// padded buffer holds Z and (after the trailing barrier) `emit(k, X)` has been called by the owning threads for
-// k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
-// Body of the forward real FFT of one frame whose pass-0 operands are already in registers (v[e] = z[load_index<0>(t, e)]):
-// lets a caller fetch the next frame from global memory while this one is being transformed.
-template <int LOG2M, class Emit, class EmitNy>
-__device__ __forceinline__ void forward_frame_regs(float2 *buf, const float2 *tw, int t, bool active, float2 (&v)[RegFft<LOG2M>::E],
-                                                   Emit emit, EmitNy emit_ny)
-{
-    using F = RegFft<LOG2M>;
-    constexpr int M = F::M;
-    F::template compute<0>(v, tw, t);
-    smem_store<LOG2M, 0>(buf, v, t);
-    group_sync<LOG2M>();
-    SmemPasses<LOG2M, 1, F::PASSES - 1>::run(buf, tw, t);
-    if (active) {
-        for (int k = t; k <= M / 2; k += F::G) {
-            if (k == 0) {
-                const float2 z0 = buf[0];
-                emit(0, make_float2(2.0f * (z0.x + z0.y), 0.0f));
-                emit_ny(2.0f * (z0.x - z0.y));
-            } else {
-                const int j = M - k;
-                const float2 a = buf[pad16(k)], b = buf[pad16(j)];
-                const float er = a.x + b.x, ei = a.y - b.y;   // E = Z[k] + conj(Z[M-k])
-                const float dr = a.x - b.x, di = a.y + b.y;   // D = Z[k] - conj(Z[M-k])
-                const float2 w = tw[k];                       // exp(-2*pi*i*k/N)
-                const float tr = w.x * dr - w.y * di, ti = w.x * di + w.y * dr;
-                emit(k, make_float2(er + ti, ei - tr));
-                if (j != k) emit(j, make_float2(er - ti, -ei - tr));
-            }
-        }
-    }
-    group_sync<LOG2M>();
-}
-
-// Forward real FFT of one frame.  `load(i)` returns z[i] = x[2i] + i*x[2i+1] of the frame (i < M); `emit(k, X)` is called
-// by the owning threads for k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
-template <int LOG2M, class Load, class Emit, class EmitNy>
-__device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int t, bool active, Load load, Emit emit, EmitNy emit_ny)
-{
-    using F = RegFft<LOG2M>;
-    float2 v[F::E];
-#pragma unroll
-    for (int e = 0; e < F::E; ++e) v[e] = active ? load(F::template load_index<0>(t, e), e) : make_float2(0.f, 0.f);
-    forward_frame_regs<LOG2M>(buf, tw, t, active, v, emit, emit_ny);
-}
-
-// Inverse real FFT: the padded buffer holds the packed spectrum acc[0..M) (acc[0].x = DC) and ny the Nyquist value;
-// `emit(i, x0, x1)` receives the time samples x[2i], x[2i+1] for i in [M/2, M) — the overlap-save "second half".
-// All threads of the CTA must call it (barriers); `active` masks the stores only.
-template <int LOG2M, class Emit>
-__device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float2 *tw, int t, bool active, Emit emit)
-{
-    using F = RegFft<LOG2M>;
-    constexpr int M = F::M;
-    // inverse split, in place; stores conj(Z) so that the forward passes compute conj(IFFT(Z))
-    for (int k = t; k <= M / 2; k += F::G) {
-        if (k == 0) {
-            const float dc = buf[0].x;
-            buf[0] = make_float2(dc + ny, -(dc - ny));
-        } else {
-            const int j = M - k;
-            const float2 a = buf[pad16(k)], b = buf[pad16(j)];
-            const float er = a.x + b.x, ei = a.y - b.y;
-            const float dr = a.x - b.x, di = a.y + b.y;
-            const float2 w = make_float2(tw[k].x, -tw[k].y);
-            const float tr = w.x * dr - w.y * di, ti = w.x * di + w.y * dr;
-            buf[pad16(k)] = make_float2(er - ti, -(ei + tr));
-            if (j != k) buf[pad16(j)] = make_float2(er + ti, -(-ei + tr));
-        }
-    }
-    group_sync<LOG2M>();
-    SmemPasses<LOG2M, 0, F::PASSES - 2>::run(buf, tw, t);
-    {
-        constexpr int P = F::PASSES - 1;
-        float2 v[F::E];
-        smem_load<LOG2M, P>(buf, v, t);
-        F::template compute<P>(v, tw, t);
-        if (active) {
-#pragma unroll
-            for (int e = 0; e < F::E; ++e) {
-                const int i = F::template store_index<P>(t, e);
-                if (i >= M / 2) emit(i - M / 2, v[e].x, -v[e].y);
-            }
-        }
-    }
-    group_sync<LOG2M>();
-}
-
-__device__ __forceinline__ float group_sum(float v, int width)   // deterministic butterfly sum over `width` (<= 32) lanes
-{
-    for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// Nyquist product sum for one (stream, ear): sum_{s,p} fdl_ny[stream][s][(head+p)%P] * bank_ny[s][p][ear], computed by
-// the G threads of a transform.  part_s: G floats of scratch for this transform.  Result valid in every thread after
-// the two barriers inside.
-template <int G>
-__device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fdl_ny, const float *bank_ny, int stream, int ear,
-                                             bool active, int t, float *part_s)
-{
-    float sum = 0.f;
-    if (active) {
-        const int terms = g.S * g.P;
-        for (int i0 = t; i0 < terms; i0 += 8 * G) {     // 8 independent load pairs in flight per thread
-            float xa[8], ha[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = i0 + k * G;
-                xa[k] = 0.f; ha[k] = 0.f;
-                if (i < terms) {
-                    const int s = i / g.P, p = i - s * g.P;
-                    int slot = g.head + p;
-                    if (slot >= g.P) slot -= g.P;
-                    xa[k] = fdl_ny[((size_t)stream * g.Se + s) * g.P_cap + slot];
-                    ha[k] = bank_ny[(size_t)i * 2 + ear];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) sum = fmaf(xa[k], ha[k], sum);
-        }
-    }
-    if constexpr (G <= 32) {
-        return group_sum(sum, G);
-    } else {
-        part_s[t] = sum;
-        __syncthreads();
-        float acc = 0.f;
-        if (t < 32) {
-            for (int i = t; i < G; i += 32) acc += part_s[i];
-        }
-        acc = group_sum(acc, 32);
-        if (t == 0) part_s[0] = acc;
-        __syncthreads();
-        return part_s[0];
-    }
-}
 
 template <int LOG2M>
 struct Geo {
@@ -286,6 +98,8 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_bank_build(const Ban
     const int se = active ? job / a.P : 0, p = active ? job - se * a.P : 0;
     const float *h = a.ir + (size_t)se * a.taps;
     const float scale = 0.25f / (float)(2 * M);   // ConvolutionEngine.swift:356, folded into the bank (exact: power of two)
+    // bank row (s, p): two planes of B/2 float4 {L.re, L.im, R.re, R.im} — even bins, then odd bins — so that the thread owning
+    // bins (2j, 2j+1) reads plane0[j] and plane1[j]: coalesced in HBM and conflict-free in shared memory
     float *dst = reinterpret_cast<float *>(a.bank + ((size_t)(se >> 1) * a.P + p) * M) + 2 * (se & 1);
     float *dst_ny = a.bank_ny + ((size_t)(se >> 1) * a.P + p) * 2 + (se & 1);
     forward_frame<LOG2M>(
@@ -299,7 +113,10 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_bank_build(const Ban
             }
             return v;
         },
-        [&](int k, float2 x) { dst[4 * k] = x.x * scale; dst[4 * k + 1] = x.y * scale; },
+        [&](int k, float2 x) {
+            float *d = dst + 4 * ((k & 1) * (M / 2) + (k >> 1));
+            d[0] = x.x * scale; d[1] = x.y * scale;
+        },
         [&](float ny) { *dst_ny = ny * scale; });
 }
 
@@ -315,22 +132,6 @@ struct IrfftArgs {
     const float2 *tw;
 };
 
-__device__ __forceinline__ void store_pair(const StridedOut &o, float *row, int i2, float x0, float x1)
-{
-    if (o.ring_cap > 0) {
-        int p0 = o.ring_start + i2;
-        if (p0 >= o.ring_cap) p0 -= o.ring_cap;
-        int p1 = p0 + 1;
-        if (p1 >= o.ring_cap) p1 -= o.ring_cap;
-        row[p0] = x0;
-        row[p1] = x1;
-    } else if ((reinterpret_cast<uintptr_t>(row + i2) & 7u) == 0) {
-        *reinterpret_cast<float2 *>(row + i2) = make_float2(x0, x1);
-    } else {
-        row[i2] = x0;
-        row[i2 + 1] = x1;
-    }
-}
 
 template <int LOG2M>
 __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const IrfftArgs a)
@@ -366,26 +167,11 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const Irff
 // costs registers.  Filter values (both ears of both bins = 2 x float4) are prefetched one iteration ahead
 // in registers and reused for the T streams of the tile.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-__device__ __forceinline__ void cmac2f(float4 &acc, const float4 x, const float hr0, const float hi0, const float hr1, const float hi1)
-{
-    acc.x = fmaf(x.x, hr0, acc.x); acc.x = fmaf(-x.y, hi0, acc.x);
-    acc.y = fmaf(x.x, hi0, acc.y); acc.y = fmaf(x.y, hr0, acc.y);
-    acc.z = fmaf(x.z, hr1, acc.z); acc.z = fmaf(-x.w, hi1, acc.z);
-    acc.w = fmaf(x.z, hi1, acc.w); acc.w = fmaf(x.w, hr1, acc.w);
-}
 
 constexpr int kMacStages = 3;
 
 // ring: kMacStages * T * THREADS float4.  fp[u]: FDL base of stream u at this thread's bin pair (float4 units);
-// bank_jp: bank + 2*jp.  Accumulates partitions p in [p0, p1) of every speaker into aL/aR (left/right ear, 2 bins each).
+// bank_jp: bank + jp.  Accumulates partitions p in [p0, p1) of every speaker into aL/aR (left/right ear, 2 bins each).
 template <int T, int THREADS>
 __device__ __forceinline__ void mac_phase(const BlockGeom &g, const float4 *const (&fp)[T], const float4 *bank_jp, float4 *ring,
                                           float4 (&aL)[T], float4 (&aR)[T], int p0, int p1)
@@ -416,14 +202,14 @@ __device__ __forceinline__ void mac_phase(const BlockGeom &g, const float4 *cons
     // filter walk: (s*P + p) * B float4; consecutive p are contiguous, a speaker change skips the partitions outside [p0, p1)
     const float4 *bk = bank_jp + (size_t)p0 * g.B;
     const size_t skip = (size_t)(g.P - np) * g.B;
-    float4 h0 = __ldg(bk), h1 = __ldg(bk + 1);
+    float4 h0 = __ldg(bk), h1 = __ldg(bk + halfB);   // even-bin plane, odd-bin plane
     int cstage = 0, cp = 0;
     for (int it = 0; it < total; ++it) {
         issue();
         bk += g.B;
         if (++cp == np) { cp = 0; bk += skip; }
         float4 n0 = h0, n1 = h1;
-        if (it + 1 < total) { n0 = __ldg(bk); n1 = __ldg(bk + 1); }
+        if (it + 1 < total) { n0 = __ldg(bk); n1 = __ldg(bk + halfB); }
         cp_async_wait<kMacStages - 1>();
 #pragma unroll
         for (int u = 0; u < T; ++u) {
@@ -463,7 +249,7 @@ __global__ void __launch_bounds__(kMacThreads) k_fdl_cmac(const BlockGeom g, con
     float4 aL[T], aR[T];
 #pragma unroll
     for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
-    mac_phase<T, kMacThreads>(g, fp, bank + 2 * jp, reinterpret_cast<float4 *>(smem_raw), aL, aR, 0, g.P);
+    mac_phase<T, kMacThreads>(g, fp, bank + jp, reinterpret_cast<float4 *>(smem_raw), aL, aR, 0, g.P);
 #pragma unroll
     for (int u = 0; u < T; ++u) {
         if (s0 + u <= last) {
@@ -574,7 +360,7 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
     float4 aL[T], aR[T];
 #pragma unroll
     for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
-    mac_phase<T, THREADS>(g, fp, a.bank + 2 * jp, reinterpret_cast<float4 *>(bufs), aL, aR, 0, g.P);
+    mac_phase<T, THREADS>(g, fp, a.bank + jp, reinterpret_cast<float4 *>(bufs), aL, aR, 0, g.P);
     __syncthreads();   // the ring aliases the FFT buffers
 
     // ---- phase C: accumulators -> shared, Nyquist sums, inverse FFT, overlap-save discard, output -------------
@@ -595,307 +381,6 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
         float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
         inverse_frame<LOG2M>(bufs + (size_t)f * FG::PS, ny, tw, t, active,
                              [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// KP  persistent warp-specialised block kernel (64 <= B <= 512): one CTA per SM walks over tiles of 4 streams.
-//
-//   warp 0            producer: one elected thread streams the FDL *history* rows (partitions p >= 1) of tile after
-//                     tile, plus the matching filter rows, into a deep shared-memory ring with TMA-class bulk copies
-//                     (cp.async.bulk ... mbarrier::complete_tx).  It never waits for anything but a free ring stage, so
-//                     HBM stays busy across tile boundaries and while other warps transform.
-//   MAC warps (B/2 threads)   one bin pair of the 4 streams per thread; consume ring stages (full/empty mbarriers), then
-//                     add the head partition (p = 0, just written by the FFT warps, read with plain loads).
-//   FFT warps (B/2 threads)   while the MAC warps stream the history of tile i they run the inverse transforms of tile i-1
-//                     (accumulators handed over through shared memory) and the forward transforms of tile i.
-//
-// The two latency-bound phases of KF (input FFT, inverse FFT) thereby run in the shadow of the bandwidth-bound phase.
-// Named barriers: HEAD_READY (FFT -> MAC), ACC_READY (MAC -> FFT), ACC_FREE (FFT -> MAC).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
-template <int LOG2M> struct PersistGeo {
-    static constexpr int M = 1 << LOG2M, halfB = M / 2, T = 4;
-    static constexpr int G = RegFft<LOG2M>::G;
-    static constexpr int PRODUCERS = 4;                                     // producer warps, one issuing lane each
-    static constexpr int MAC_GROUPS = 2, TG = T / MAC_GROUPS;               // two groups of MAC warps, 2 streams each
-    static constexpr int FFT_GROUPS = 1, NFT = 8 * FFT_GROUPS;             // transforms the FFT warps run side by side
-    static constexpr int MAC_THREADS = MAC_GROUPS * halfB, FFT_THREADS = FFT_GROUPS * halfB;
-    static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
-    static constexpr int PS = PaddedSize<LOG2M>::value;
-    static constexpr size_t stage_bytes = (size_t)T * halfB * sizeof(float4) + (size_t)M * sizeof(float4);   // T FDL rows + one filter row
-    static constexpr size_t fixed_bytes = (size_t)M * sizeof(float2)               // twiddles
-                                          + (size_t)(NFT + 8) * PS * sizeof(float2) // FFT buffers + accumulator hand-over buffers
-                                          + 512;                                   // mbarriers (2 x STAGES x 8 B)
-    static constexpr int max_stages = (int)((220 * 1024 - fixed_bytes) / stage_bytes);
-    static constexpr int STAGES = max_stages > 24 ? 24 : max_stages;
-    static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
-};
-
-struct PersistArgs {
-    BlockGeom g;
-    StridedIn cur, prev;
-    float *overlap_save;
-    float2 *fdl;
-    float *fdl_ny;
-    const float4 *bank;
-    const float *bank_ny;
-    StridedOut out;
-    const float2 *tw;
-    int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms
-};
-
-template <int LOG2M>
-__global__ void __launch_bounds__(PersistGeo<LOG2M>::THREADS, 1) k_persistent(const PersistArgs a)
-{
-    using PG = PersistGeo<LOG2M>;
-    constexpr int M = PG::M, halfB = PG::halfB, T = PG::T, TG = PG::TG, G = PG::G, STAGES = PG::STAGES, PS = PG::PS;
-    constexpr int BAR_HEAD_READY = 1, BAR_ACC_READY = 2, BAR_ACC_FREE = 3, PAIR = PG::MAC_THREADS + PG::FFT_THREADS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float4 *ring = reinterpret_cast<float4 *>(smem_raw);                                   // STAGES x (T*halfB + M) float4
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw + (size_t)STAGES * PG::stage_bytes);
-    float2 *fftbuf = tw + M;
-    float2 *accbuf = fftbuf + (size_t)PG::NFT * PS;
-    uint64_t *full = reinterpret_cast<uint64_t *>(accbuf + (size_t)8 * PS);
-    uint64_t *empty = full + STAGES;
-    const BlockGeom &g = a.g;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tiles = (g.n_streams + T - 1) / T;
-    const int last = g.first_stream + g.n_streams - 1;
-    const int old_iters = g.S * (g.P - 1);
-    constexpr int stage_f4 = T * halfB + M;
-
-    for (int k = tid; k < M; k += PG::THREADS) tw[k] = a.tw[k];
-    if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], PG::MAC_THREADS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    if (warp < PG::PRODUCERS) {
-        // ===== producers: warp w issues the iterations k = w, w + PRODUCERS, ... of this CTA's iteration sequence =====
-        if (lane == 0 && old_iters > 0) {
-            const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
-            const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
-            const int pm1 = g.P - 1;
-            long long k = warp;                       // global iteration index over (tile_local, s, p-1)
-            int tile = blockIdx.x;
-            int rem = warp;                           // iteration within the tile
-            while (rem >= old_iters) { rem -= old_iters; tile += gridDim.x; }
-            while (tile < n_tiles) {
-                const int s = rem / pm1, p = 1 + (rem - s * pm1);
-                int slot = g.head + p;
-                if (slot >= g.P) slot -= g.P;         // modulus is partitionCount (Q4)
-                const int stage = (int)(k % STAGES);
-                const unsigned phase = (unsigned)((k / STAGES) & 1);
-                const int s0 = g.first_stream + tile * T;
-                mbar_wait(&empty[stage], phase ^ 1u);
-                mbar_expect_tx(&full[stage], (unsigned)PG::stage_bytes);
-                float4 *dst = ring + (size_t)stage * stage_f4;
-#pragma unroll
-                for (int u = 0; u < T; ++u)
-                    bulk_g2s(dst + u * halfB, fdl4 + (size_t)min(s0 + u, last) * stream_stride + ((size_t)s * g.P_cap + slot) * halfB,
-                             (unsigned)(halfB * sizeof(float4)), &full[stage]);
-                bulk_g2s(dst + T * halfB, a.bank + ((size_t)s * g.P + p) * M, (unsigned)(M * sizeof(float4)), &full[stage]);
-                k += PG::PRODUCERS;
-                rem += PG::PRODUCERS;
-                while (rem >= old_iters) { rem -= old_iters; tile += gridDim.x; }
-            }
-        }
-    } else if (warp < PG::PRODUCERS + PG::MAC_THREADS / 32) {
-        // ===== MAC warps: group gi owns streams 2*gi, 2*gi+1 of the tile; one bin pair per thread =====
-        const int mt = tid - 32 * PG::PRODUCERS;
-        const int gi = mt / halfB, jp = mt - gi * halfB;   // bins 2*jp, 2*jp+1
-        int stage = 0;
-        unsigned phase = 0;
-        const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
-        const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
-        int local = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
-            const int s0 = g.first_stream + tile * T + gi * TG;
-            float4 aL[TG], aR[TG];
-#pragma unroll
-            for (int u = 0; u < TG; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
-            for (int it = 0; it < old_iters; ++it) {
-                mbar_wait(&full[stage], phase);
-                const float4 *src = ring + (size_t)stage * stage_f4;
-                const float4 h0 = src[T * halfB + 2 * jp], h1 = src[T * halfB + 2 * jp + 1];
-                float4 x[TG];
-#pragma unroll
-                for (int u = 0; u < TG; ++u) x[u] = src[(gi * TG + u) * halfB + jp];
-#pragma unroll
-                for (int u = 0; u < TG; ++u) {
-                    cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
-                    cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[stage]);
-                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-            }
-            // head partition (p = 0): written by this CTA's FFT warps for this very block
-            named_sync(BAR_HEAD_READY, PAIR);
-            for (int s = 0; s < g.S; ++s) {
-                const float4 h0 = __ldg(a.bank + (size_t)s * g.P * M + 2 * jp), h1 = __ldg(a.bank + (size_t)s * g.P * M + 2 * jp + 1);
-                const size_t off = ((size_t)s * g.P_cap + g.head) * halfB + jp;
-                float4 x[TG];
-#pragma unroll
-                for (int u = 0; u < TG; ++u) x[u] = *(fdl4 + (size_t)min(s0 + u, last) * stream_stride + off);
-#pragma unroll
-                for (int u = 0; u < TG; ++u) {
-                    cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
-                    cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
-                }
-            }
-            if (local > 0) named_sync(BAR_ACC_FREE, PAIR);   // the FFT warps are done with the previous accumulators
-#pragma unroll
-            for (int u = 0; u < TG; ++u) {
-                float2 *bl = accbuf + (size_t)(2 * (gi * TG + u)) * PS, *br = bl + PS;
-                bl[pad16(2 * jp)] = make_float2(aL[u].x, aL[u].y);
-                bl[pad16(2 * jp + 1)] = make_float2(aL[u].z, aL[u].w);
-                br[pad16(2 * jp)] = make_float2(aR[u].x, aR[u].y);
-                br[pad16(2 * jp + 1)] = make_float2(aR[u].z, aR[u].w);
-            }
-            __threadfence_block();
-            named_arrive(BAR_ACC_READY, PAIR);
-        }
-    } else {
-        // ===== FFT warps =====
-        const int ft = tid - 32 * PG::PRODUCERS - PG::MAC_THREADS;
-        const int f = ft / G, t = ft % G;
-        auto inverse_tile = [&](int tile) {
-            const int s0 = g.first_stream + tile * T;
-            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
-            if (f >= 8) return;                 // 2*T = 8 inverse transforms; transforms never share a warp with f < 8 (8*G >= 32)
-            const int ls = f >> 1, ear = f & 1;
-            const bool active = ls < nvalid;
-            const int stream = s0 + (active ? ls : 0);
-            const float ny = nyquist_sum<G>(g, a.fdl_ny, a.bank_ny, stream, ear, active, t, nullptr);
-            float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
-            inverse_frame<LOG2M>(accbuf + (size_t)f * PS, ny, tw, t, active,
-                                 [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
-        };
-        int local = 0, prev_tile = -1;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++local) {
-            if (local > 0) {
-                named_sync(BAR_ACC_READY, PAIR);
-                if (!(a.debug & 2)) inverse_tile(prev_tile);
-                __syncwarp();
-                named_arrive(BAR_ACC_FREE, PAIR);
-            }
-            const int s0 = g.first_stream + tile * T;
-            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
-            const int nfft = T * g.S;
-            using F = RegFft<LOG2M>;
-            // round r transforms frames r*8 + f; the operands of round r+1 are fetched before round r is transformed
-            auto fetch = [&](int base, float2 (&v)[F::E], bool &active, int &stream, int &s) {
-                const int idx = base + f;
-                const int ls = idx / g.S;
-                s = idx - ls * g.S;
-                active = idx < nfft && ls < nvalid;
-                stream = s0 + (active ? ls : 0);
-                const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
-                const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
-#pragma unroll
-                for (int e = 0; e < F::E; ++e) {
-                    const int i = F::template load_index<0>(t, e);
-                    v[e] = !active ? make_float2(0.f, 0.f)
-                                   : (i < M / 2 ? *reinterpret_cast<const float2 *>(prev + 2 * i) : *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2)));
-                }
-            };
-            float2 v[F::E], vn[F::E];
-            bool active = false, active_n = false;
-            int stream = 0, sp = 0, stream_n = 0, sp_n = 0;
-            const int base0 = (a.debug & 1) ? nfft : 0;
-            if (base0 < nfft) fetch(base0, v, active, stream, sp);
-            for (int base = base0; base < nfft; base += PG::NFT) {
-                if (base + PG::NFT < nfft) fetch(base + PG::NFT, vn, active_n, stream_n, sp_n);
-                if (active && a.overlap_save) {   // inputOverlapBuffer <- current block (the same thread read these addresses as `prev`)
-                    float *ov = a.overlap_save + ((size_t)stream * g.Se + sp) * M;
-#pragma unroll
-                    for (int e = 0; e < F::E; ++e) {
-                        const int i = F::template load_index<0>(t, e);
-                        if (i >= M / 2) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v[e];
-                    }
-                }
-                const size_t row = ((size_t)stream * g.Se + sp) * g.P_cap + g.head;
-                float2 *dst = a.fdl + row * M;
-                float *dst_ny = a.fdl_ny + row;
-                forward_frame_regs<LOG2M>(fftbuf + (size_t)f * PS, tw, t, active, v,
-                                          [&](int k, float2 x) { dst[k] = x; }, [&](float ny) { *dst_ny = ny; });
-#pragma unroll
-                for (int e = 0; e < F::E; ++e) v[e] = vn[e];
-                active = active_n; stream = stream_n; sp = sp_n;
-            }
-            __threadfence_block();
-            named_arrive(BAR_HEAD_READY, PAIR);
-            prev_tile = tile;
-        }
-        if (prev_tile >= 0) {
-            named_sync(BAR_ACC_READY, PAIR);
-            if (!(a.debug & 2)) inverse_tile(prev_tile);
-        }
-    }
-}
-
-template <int LOG2M>
-cudaError_t launch_persistent_l(const PersistArgs &a, int ctas, cudaStream_t st)
-{
-    static bool configured = false;   // opt in to the large dynamic shared memory once per process
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(k_persistent<LOG2M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PersistGeo<LOG2M>::smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    k_persistent<LOG2M><<<ctas, PersistGeo<LOG2M>::THREADS, PersistGeo<LOG2M>::smem, st>>>(a);
-    return cudaGetLastError();
-}
-
-bool persistent_supported(int log2m, int P) { return log2m >= 6 && log2m <= 9 && P >= 1; }
-
-cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
-                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int num_sms, int debug,
-                              cudaStream_t st)
-{
-    if (g.n_streams <= 0) return cudaSuccess;
-    PersistArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, bank, bank_ny, out, tw, debug};
-    const int tiles = (g.n_streams + 3) / 4;
-    const int ctas = tiles < num_sms ? tiles : num_sms;
-    switch (g.log2m) {
-    case 6: return launch_persistent_l<6>(a, ctas, st);
-    case 7: return launch_persistent_l<7>(a, ctas, st);
-    case 8: return launch_persistent_l<8>(a, ctas, st);
-    case 9: return launch_persistent_l<9>(a, ctas, st);
-    default: return cudaErrorInvalidValue;
     }
 }
 

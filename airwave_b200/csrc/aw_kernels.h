@@ -32,6 +32,7 @@ struct StridedOut {     // planar output; when ring_cap > 0 sample i lands at (r
 // K2: [prev | cur] -> real FFT -> FDL slot `head` (+ Nyquist side array); optionally saves cur as next overlap.
 cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl,
                               float *fdl_ny, const float2 *tw, cudaStream_t st);
+// Filter bank layout: row (s, p) = two planes of B/2 float4 {L.re, L.im, R.re, R.im}: even bins, then odd bins.
 // K3: acc[stream][ear][bin] = sum_{s,p} FDL[stream][s][(head+p)%P][bin] * bank[s][p][bin].ear
 cudaError_t launch_fdl_cmac(const BlockGeom &g, const float2 *fdl, const float4 *bank, float2 *acc, int tile, cudaStream_t st);
 // K4: Nyquist reduction + inverse real FFT + overlap-save discard -> out (planar or FIFO ring)
@@ -79,11 +80,12 @@ int fused_blocks_per_sm(int log2m, int tile);   // resident CTAs per SM of that 
 cudaError_t launch_fused(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
                          const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, cudaStream_t st);
 
-// KP: persistent warp-specialised variant of KF (one CTA per SM, TMA bulk-copy ring, FFT warps overlapped with MAC warps).
-bool persistent_supported(int log2m, int P);
+// KP: persistent warp-specialised block kernel (aw_persistent.cu): one CTA per SM, TMA bulk-copy ring, FFT warps one tile
+// ahead of the MAC warps; 64 <= B <= 2048.  `tile` = streams per tile (4 or 2).
+int persistent_tiles(int log2m);                // bit mask of the tiles available for that transform size (0 = unsupported)
 cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
-                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int num_sms, int debug,
-                              cudaStream_t st);
+                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
+                              int debug, cudaStream_t st);
 
 size_t fft_smem_bytes(int log2m);
 cudaError_t configure_kernels(int log2m);   // opt in to > 48 KB dynamic shared memory for that transform size

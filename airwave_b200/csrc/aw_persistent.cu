@@ -1,0 +1,390 @@
+// aw_persistent.cu — KP: the persistent warp-specialised block kernel (64 <= B <= 2048), the default hot path.
+//
+// One CTA per SM walks over tiles of T streams (T = 4 or 2).  For every tile it does what 2*S ConvolutionEngine.process
+// calls plus the RealtimeAudioProcessor mix do for T streams (ConvolutionEngine.swift:232-367, RealtimeAudioProcessor.swift:
+// 146-163): forward real FFT of the T*S overlap-save frames, frequency-domain delay-line multiply-accumulate over all
+// (speaker, partition) pairs for both ears, inverse real FFT with the overlap-save discard.
+//
+//   warp 0 (producer)   streams FDL rows and the matching filter rows into a deep shared-memory ring with TMA-class
+//                       bulk copies (cp.async.bulk ... mbarrier::complete_tx); every lane issues one copy of a stage, so
+//                       a stage of up to 20 copies costs one instruction slot.  A stage holds R (speaker, partition)
+//                       pairs x C bin pairs for the T streams: C = min(B/2, 128) and R = 128/C, i.e. always 128 bin-pair
+//                       lanes of work per stream group whatever the block size.  Rows wider than 128 bin pairs are walked
+//                       in column chunks (accumulators stay in registers for the whole chunk).
+//   8 MAC warps         two groups of 128 threads, T/2 streams each; a thread owns one bin pair (two complex bins, one
+//                       float4 of FDL) of one row of the stage, both ears.  full/empty mbarriers per stage.  With R > 1
+//                       the R partial sums are reduced through shared memory in a fixed order (deterministic).
+//   4 or 8 FFT warps    run the forward transforms ONE TILE AHEAD of the MAC warps (nothing but the head slot of the FDL
+//                       depends on them), and the inverse transforms of the tile the MAC warps just finished
+//                       (accumulators handed over through shared memory, acc_ready/acc_free mbarriers).
+//
+// The head partition (p = 0) is streamed like any other row: the FFT warps publish it with a generic->async proxy fence
+// + the head_ready mbarrier, which the producer waits on before it issues the first head row of a tile.
+// Pair order inside a tile: all (s, p >= 1) pairs speaker-major, then the S head pairs — the same for every tile size and
+// stream count, so a stream's output does not depend on how many streams the engine renders or on which GPU it lives.
+#include "aw_fft_blocks.cuh"
+
+namespace aw {
+
+template <int LOG2M, int T> struct PGeo {
+    static_assert(T == 2 || T == 4, "tile of 2 or 4 streams");
+    static constexpr int M = 1 << LOG2M, halfB = M / 2;
+    static constexpr int C = halfB < 128 ? halfB : 128;      // bin pairs per column chunk
+    static constexpr int NC = halfB / C;                     // column chunks per row
+    static constexpr int R = 128 / C;                        // (speaker, partition) pairs per stage
+    static constexpr int MAC_GROUPS = 2, TG = T / MAC_GROUPS;
+    static constexpr int MAC_THREADS = MAC_GROUPS * 128;
+    static constexpr int G = RegFft<LOG2M>::G;               // threads per transform
+    static constexpr int FFT_THREADS = 8 * G <= 128 ? 128 : 256;
+    static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
+    static constexpr int THREADS = 32 + MAC_THREADS + FFT_THREADS;
+    static constexpr int PS = PaddedSize<LOG2M>::value;
+    static constexpr int stage_f4 = R * (T + 2) * C;         // R x (T FDL rows + 2 filter planes) x C float4
+    static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
+    static constexpr int CPR = T + (NC == 1 ? 1 : 2);        // bulk copies per pair
+    static constexpr int red_f4 = (R - 1) * T * 2 * C;       // partial sums of rows 1..R-1
+    static constexpr size_t fixed_bytes = (size_t)M * sizeof(float2)                    // twiddles
+                                          + (size_t)(NFT + 2 * T) * PS * sizeof(float2)  // forward buffers + accumulator buffers
+                                          + (size_t)red_f4 * sizeof(float4) + (size_t)FFT_THREADS * sizeof(float) + 1024;
+    static constexpr int max_stages = (int)((226 * 1024 - fixed_bytes) / stage_bytes);
+    static constexpr int STAGES = max_stages > 32 ? 32 : max_stages;
+    static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
+    static constexpr bool PREFETCH = LOG2M <= 8;             // next round's operands fetched while this round transforms
+    static_assert(R * CPR <= 32, "one lane per bulk copy");
+    static_assert(STAGES >= 4, "ring too shallow");
+};
+
+struct PersistArgs {
+    BlockGeom g;
+    StridedIn cur, prev;
+    float *overlap_save;
+    float2 *fdl;
+    float *fdl_ny;
+    const float4 *bank;
+    const float *bank_ny;
+    StridedOut out;
+    const float2 *tw;
+    int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms
+};
+
+// (speaker, partition) of pair `idx`: history pairs first (speaker-major, p = 1..P-1), then the S head pairs.
+__device__ __forceinline__ void pair_sp(int idx, int S, int P, int &s, int &p)
+{
+    const int hist = S * (P - 1);
+    if (idx < hist) { s = idx / (P - 1); p = 1 + idx - s * (P - 1); }
+    else { s = idx - hist; p = 0; }
+}
+
+template <int LOG2M, int T>
+__global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const PersistArgs a)
+{
+    using PG = PGeo<LOG2M, T>;
+    constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, TG = PG::TG, G = PG::G, NFT = PG::NFT;
+    constexpr int STAGES = PG::STAGES, PS = PG::PS, stage_f4 = PG::stage_f4, CPR = PG::CPR;
+    constexpr int MAC_WARPS = PG::MAC_THREADS / 32, FFT_WARPS = PG::FFT_THREADS / 32;
+    constexpr int BAR_RED_A = 1, BAR_RED_B = 2, BAR_FFT0 = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float4 *ring = reinterpret_cast<float4 *>(smem_raw);
+    float2 *tw = reinterpret_cast<float2 *>(smem_raw + (size_t)STAGES * PG::stage_bytes);
+    float2 *fftbuf = tw + M;
+    float2 *accbuf = fftbuf + (size_t)NFT * PS;
+    float4 *red = reinterpret_cast<float4 *>(accbuf + (size_t)2 * T * PS);
+    float *part = reinterpret_cast<float *>(red + PG::red_f4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(part + PG::FFT_THREADS);
+    uint64_t *empty = full + STAGES;
+    uint64_t *head_ready = empty + STAGES;   // [2], alternating by local tile parity
+    uint64_t *acc_ready = head_ready + 2;
+    uint64_t *acc_free = acc_ready + 1;
+
+    const BlockGeom &g = a.g;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_tiles = (g.n_streams + T - 1) / T;
+    const int last = g.first_stream + g.n_streams - 1;
+    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_pairs = g.S * g.P;
+    const int spc = (n_pairs + R - 1) / R;               // stages per column chunk
+    const int head_stage = g.S * (g.P - 1) / R;          // first stage of a chunk that holds a head pair
+
+    for (int k = tid; k < M; k += PG::THREADS) tw[k] = a.tw[k];
+    if (tid == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MAC_WARPS); }
+        mbar_init(&head_ready[0], FFT_WARPS);
+        mbar_init(&head_ready[1], FFT_WARPS);
+        mbar_init(acc_ready, MAC_WARPS);
+        mbar_init(acc_free, FFT_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ===== producer =====
+        const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+        const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
+        int stage = 0;
+        unsigned phase = 0;
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
+            for (int c = 0; c < NC; ++c) {
+                for (int j = 0; j < spc; ++j) {
+                    if (c == 0 && j == head_stage) mbar_wait(&head_ready[lt & 1], (unsigned)((lt >> 1) & 1));
+                    if (lane == 0) mbar_wait(&empty[stage], phase ^ 1u);
+                    __syncwarp();
+                    const int nrows = min(R, n_pairs - j * R);
+                    if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)(nrows * (T + 2) * C * sizeof(float4)));
+                    __syncwarp();
+                    if (lane < nrows * CPR) {
+                        const int r = lane / CPR, q = lane - r * CPR;
+                        int s, p;
+                        pair_sp(j * R + r, g.S, g.P, s, p);
+                        int slot = g.head + p;
+                        if (slot >= g.P) slot -= g.P;                  // modulus is partitionCount (Q4)
+                        float4 *dst = ring + (size_t)stage * stage_f4;
+                        if (q < T) {
+                            bulk_g2s(dst + (r * T + q) * C,
+                                     fdl4 + (size_t)min(s0 + q, last) * stream_stride + ((size_t)s * g.P_cap + slot) * halfB + c * C,
+                                     (unsigned)(C * sizeof(float4)), &full[stage]);
+                        } else if (NC == 1) {                          // both planes of the filter row are contiguous
+                            bulk_g2s(dst + R * T * C + r * 2 * C, a.bank + ((size_t)s * g.P + p) * M, (unsigned)(2 * C * sizeof(float4)),
+                                     &full[stage]);
+                        } else {
+                            const int pl = q - T;
+                            bulk_g2s(dst + R * T * C + (r * 2 + pl) * C, a.bank + ((size_t)s * g.P + p) * M + pl * halfB + c * C,
+                                     (unsigned)(C * sizeof(float4)), &full[stage]);
+                        }
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp < 1 + MAC_WARPS) {
+        // ===== MAC warps =====
+        const int mt = tid - 32;
+        const int gi = mt >> 7, w = mt & 127;
+        const int r = w / C, jp = w - r * C;
+        int stage = 0;
+        unsigned phase = 0;
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            for (int c = 0; c < NC; ++c) {
+                float4 aL[TG], aR[TG];
+#pragma unroll
+                for (int u = 0; u < TG; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
+                for (int j = 0; j < spc; ++j) {
+                    mbar_wait(&full[stage], phase);
+                    if (r < n_pairs - j * R) {
+                        const float4 *src = ring + (size_t)stage * stage_f4;
+                        const float4 h0 = src[R * T * C + (r * 2) * C + jp], h1 = src[R * T * C + (r * 2 + 1) * C + jp];
+                        float4 x[TG];
+#pragma unroll
+                        for (int u = 0; u < TG; ++u) x[u] = src[(r * T + gi * TG + u) * C + jp];
+#pragma unroll
+                        for (int u = 0; u < TG; ++u) {
+                            cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
+                            cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                // the FFT warps must be done with the previous tile's accumulators before they are overwritten
+                if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
+                if constexpr (R > 1) {
+                    if (r > 0) {
+#pragma unroll
+                        for (int u = 0; u < TG; ++u) {
+                            float4 *d = red + ((size_t)(((r - 1) * PG::MAC_GROUPS + gi) * TG + u) * 2) * C + jp;
+                            d[0] = aL[u];
+                            d[C] = aR[u];
+                        }
+                    }
+                    named_sync(BAR_RED_A, PG::MAC_THREADS);
+                    if (r == 0) {
+#pragma unroll
+                        for (int rr = 1; rr < R; ++rr) {
+#pragma unroll
+                            for (int u = 0; u < TG; ++u) {
+                                const float4 *d = red + ((size_t)(((rr - 1) * PG::MAC_GROUPS + gi) * TG + u) * 2) * C + jp;
+                                const float4 l = d[0], rt = d[C];
+                                aL[u].x += l.x; aL[u].y += l.y; aL[u].z += l.z; aL[u].w += l.w;
+                                aR[u].x += rt.x; aR[u].y += rt.y; aR[u].z += rt.z; aR[u].w += rt.w;
+                            }
+                        }
+                    }
+                    named_sync(BAR_RED_B, PG::MAC_THREADS);
+                }
+                if (r == 0) {
+                    const int J = c * C + jp;   // bins 2J, 2J+1
+#pragma unroll
+                    for (int u = 0; u < TG; ++u) {
+                        float2 *bl = accbuf + (size_t)(2 * (gi * TG + u)) * PS, *br = bl + PS;
+                        bl[pad16(2 * J)] = make_float2(aL[u].x, aL[u].y);
+                        bl[pad16(2 * J + 1)] = make_float2(aL[u].z, aL[u].w);
+                        br[pad16(2 * J)] = make_float2(aR[u].x, aR[u].y);
+                        br[pad16(2 * J + 1)] = make_float2(aR[u].z, aR[u].w);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_ready);
+        }
+    } else {
+        // ===== FFT warps =====
+        using F = RegFft<LOG2M>;
+        const int ft = tid - 32 - PG::MAC_THREADS;
+        const int f = ft / G, t = ft - f * G;
+        const int warp_first_f = G >= 32 ? f : (ft - lane) / G;   // first transform handled by this warp
+        const GroupBar gb{BAR_FFT0 + f, G};
+        float *my_part = part + (size_t)f * G;
+
+        auto forward_tile = [&](int lt) {
+            const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
+            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
+            const int nfft = T * g.S;
+            if (!(a.debug & 1)) {
+                auto fetch = [&](int base, float2 (&v)[F::E], bool &active, int &stream, int &s) {
+                    const int idx = base + f;
+                    const int ls = idx / g.S;
+                    s = idx - ls * g.S;
+                    active = idx < nfft && ls < nvalid;
+                    stream = s0 + (active ? ls : 0);
+                    const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
+                    const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
+#pragma unroll
+                    for (int e = 0; e < F::E; ++e) {
+                        const int i = F::template load_index<0>(t, e);   // frame = [previous block | current block] (:237-248)
+                        v[e] = !active ? make_float2(0.f, 0.f)
+                                       : (i < M / 2 ? *reinterpret_cast<const float2 *>(prev + 2 * i) : *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2)));
+                    }
+                };
+                auto transform = [&](float2 (&v)[F::E], bool active, int stream, int sp) {
+                    if (active && a.overlap_save) {   // inputOverlapBuffer <- current block (:243); this thread read the same addresses as `prev`
+                        float *ov = a.overlap_save + ((size_t)stream * g.Se + sp) * M;
+#pragma unroll
+                        for (int e = 0; e < F::E; ++e) {
+                            const int i = F::template load_index<0>(t, e);
+                            if (i >= M / 2) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v[e];
+                        }
+                    }
+                    const size_t row = ((size_t)stream * g.Se + sp) * g.P_cap + g.head;
+                    float2 *dst = a.fdl + row * M;
+                    float *dst_ny = a.fdl_ny + row;
+                    forward_frame_regs<LOG2M>(fftbuf + (size_t)f * PS, tw, t, active, v,
+                                              [&](int k, float2 x) { dst[k] = x; }, [&](float ny) { *dst_ny = ny; }, gb);   // FDL[head] <- spectrum (:256-264)
+                };
+                float2 v[F::E];
+                bool active = false;
+                int stream = 0, sp = 0;
+                if constexpr (PG::PREFETCH) {
+                    float2 vn[F::E];
+                    bool active_n = false;
+                    int stream_n = 0, sp_n = 0;
+                    fetch(0, v, active, stream, sp);
+                    for (int base = 0; base < nfft; base += NFT) {
+                        if (base + NFT < nfft) fetch(base + NFT, vn, active_n, stream_n, sp_n);
+                        transform(v, active, stream, sp);
+#pragma unroll
+                        for (int e = 0; e < F::E; ++e) v[e] = vn[e];
+                        active = active_n; stream = stream_n; sp = sp_n;
+                    }
+                } else {
+                    for (int base = 0; base < nfft; base += NFT) {
+                        fetch(base, v, active, stream, sp);
+                        transform(v, active, stream, sp);
+                    }
+                }
+            }
+            // publish the head slots: generic-proxy global writes -> visible to the producer's async-proxy bulk reads
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&head_ready[lt & 1]);
+        };
+
+        auto inverse_tile = [&](int lt) {
+            const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
+            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
+            for (int base = 0; base < 2 * T; base += NFT) {
+                if (base + warp_first_f >= 2 * T) continue;          // warp-uniform: no transform of this warp has work
+                const int idx = base + f;
+                const int ls = idx >> 1, ear = idx & 1;
+                const bool active = idx < 2 * T && ls < nvalid;
+                const int stream = s0 + (active ? ls : 0);
+                // idle transforms of a working warp run on their (free) forward buffer so the warp stays converged
+                float2 *buf = idx < 2 * T ? accbuf + (size_t)idx * PS : fftbuf + (size_t)f * PS;
+                const float ny = nyquist_sum<G>(g, a.fdl_ny, a.bank_ny, stream, ear, active, t, my_part, gb);
+                float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
+                inverse_frame<LOG2M>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
+            }
+        };
+
+        if (my_tiles > 0) forward_tile(0);
+        for (int lt = 0; lt < my_tiles; ++lt) {
+            if (lt + 1 < my_tiles) forward_tile(lt + 1);
+            mbar_wait(acc_ready, (unsigned)(lt & 1));
+            if (!(a.debug & 2)) inverse_tile(lt);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_free);
+        }
+    }
+}
+
+namespace {
+
+template <int LOG2M, int T>
+cudaError_t launch_persistent_lt(const PersistArgs &a, int ctas, cudaStream_t st)
+{
+    static bool configured[64] = {};   // opt in to the large dynamic shared memory once per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_persistent<LOG2M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGeo<LOG2M, T>::smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    k_persistent<LOG2M, T><<<ctas, PGeo<LOG2M, T>::THREADS, PGeo<LOG2M, T>::smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// tiles supported for a transform size, as a bit mask of T
+int persistent_tiles(int log2m)
+{
+    if (log2m >= 6 && log2m <= 10) return 4 | 2;
+    if (log2m == 11) return 2;
+    return 0;
+}
+
+cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
+                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
+                              int debug, cudaStream_t st)
+{
+    if (g.n_streams <= 0) return cudaSuccess;
+    if (!(persistent_tiles(g.log2m) & tile)) return cudaErrorInvalidValue;
+    PersistArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, bank, bank_ny, out, tw, debug};
+    const int tiles = (g.n_streams + tile - 1) / tile;
+    const int ctas = tiles < max_ctas ? tiles : max_ctas;
+#define AW_KP(L, TT) return launch_persistent_lt<L, TT>(a, ctas, st)
+    if (tile == 4) {
+        switch (g.log2m) {
+        case 6: AW_KP(6, 4);
+        case 7: AW_KP(7, 4);
+        case 8: AW_KP(8, 4);
+        case 9: AW_KP(9, 4);
+        case 10: AW_KP(10, 4);
+        default: return cudaErrorInvalidValue;
+        }
+    }
+    switch (g.log2m) {
+    case 6: AW_KP(6, 2);
+    case 7: AW_KP(7, 2);
+    case 8: AW_KP(8, 2);
+    case 9: AW_KP(9, 2);
+    case 10: AW_KP(10, 2);
+    case 11: AW_KP(11, 2);
+    default: return cudaErrorInvalidValue;
+    }
+#undef AW_KP
+}
+
+}  // namespace aw

@@ -42,6 +42,8 @@ WORKLOADS = {
     "C2": ("7.1->binaural, RoomSH1.0 HeSuVi 14-ch HRIR (4320 taps), B=256, 4096 streams/GPU", 8, 256, 4096, "RoomSH1.0"),
     "C1": ("stereo->binaural, NeutralSH1.0, B=512, single stream", 2, 512, 1, "NeutralSH1.0"),
     "C3": ("7.1->binaural, synthetic 65,536-tap BRIR, B=512, 1024 streams/GPU", 8, 512, 1024, "synthetic65536"),
+    "C4": ("full chain: 7.1->binaural with StageSH1.0 relabelled 44.1 kHz and resampled to 48 kHz (4320 -> 4702 taps), B=256, "
+           "+ 10-band parametric EQ (CCA CRA fixture), 8192 streams/GPU", 8, 256, 8192, "StageSH1.0@44100"),
     "C5-64": ("7.1->binaural, RoomSH1.0, B=64, 2048 streams/GPU", 8, 64, 2048, "RoomSH1.0"),
     "C5-128": ("7.1->binaural, RoomSH1.0, B=128, 2048 streams/GPU", 8, 128, 2048, "RoomSH1.0"),
     "C5-512": ("7.1->binaural, RoomSH1.0, B=512, 2048 streams/GPU", 8, 512, 2048, "RoomSH1.0"),
@@ -61,8 +63,31 @@ def hrir_pcm(name: str):
         pcm[:, 190] += 0.5
         return pcm, FS
     import airwave_b200 as aw
+    name, _, relabel = name.partition("@")      # "preset@rate": treat the file as a source of that sample rate
     wav = aw.WAVLoader.load(os.path.join(GOLDEN, "hrtf", name + ".wav"))
-    return wav.audioData, wav.sampleRate
+    return wav.audioData, (float(relabel) if relabel else wav.sampleRate)
+
+
+def eq_definition_for(workload: str, parser):
+    """C4 carries the reference's 10-filter fixture (AirwaveTests/Fixtures/CCA CRA ParametricEq.txt); others have no EQ."""
+    if workload != "C4":
+        return None
+    with open(os.path.join(GOLDEN, "eq", "CCA CRA ParametricEq.txt"), "rb") as f:
+        return parser(f.read(), "CCA CRA ParametricEq.txt")
+
+
+def recorded_traffic(workload: str, kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture (profiles/), or None."""
+    best = None
+    try:
+        for name in sorted(os.listdir(os.path.join(ROOT, "profiles"))):
+            if name.endswith("_traffic.json"):
+                rec = json.load(open(os.path.join(ROOT, "profiles", name))).get(workload)
+                if rec and rec.get("kernel") == kernel:
+                    best = float(rec["dram_bytes_read"]) + float(rec["dram_bytes_write"])
+    except Exception:
+        return None
+    return best
 
 
 def speaker_maps(S: int):
@@ -72,9 +97,9 @@ def speaker_maps(S: int):
     return [m.getIndices(s)[0] for s in lay.channels], [m.getIndices(s)[1] for s in lay.channels]
 
 
-def algorithmic_bytes(S: int, B: int, P: int) -> int:
-    """per stream per block, FDL ring (1 slot written + P-1 read) + input + output."""
-    return 8 * S * B * P + 4 * S * B + 8 * B
+def algorithmic_bytes(S: int, B: int, P: int, eq_filters: int = 0) -> int:
+    """per stream per block, FDL ring (1 slot written + P-1 read) + input + output [+ EQ state]."""
+    return 8 * S * B * P + 4 * S * B + 8 * B + 32 * eq_filters
 
 
 def measured_peaks():
@@ -129,14 +154,25 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_sample(S, B, pcm, l_idx, r_idx, budget_s, threads=0):
+def cpu_filters(S, pcm, rate, l_idx, r_idx):
+    """[S][2][taps] impulse responses the reference would build its engines from (resampled like Resampler.swift when rates differ)."""
+    import numpy as np
+    import oracle
+    chans = {}
+    for c in set(l_idx) | set(r_idx):
+        chans[c] = pcm[c] if abs(rate - FS) < 0.01 else oracle.resample_high_quality(pcm[c], rate, FS)
+    taps = len(next(iter(chans.values())))
+    h = np.zeros((S, 2, taps), np.float32)
+    for s in range(S):
+        h[s, 0], h[s, 1] = chans[l_idx[s]], chans[r_idx[s]]
+    return h
+
+
+def cpu_sample(S, B, pcm, rate, l_idx, r_idx, budget_s, threads=0):
     """Times the oracle (C restatement of the reference) on a bounded sample of the workload."""
     import numpy as np
     import oracle
-    taps = pcm.shape[1]
-    h = np.zeros((S, 2, taps), np.float32)
-    for s in range(S):
-        h[s, 0], h[s, 1] = pcm[l_idx[s]], pcm[r_idx[s]]
+    h = cpu_filters(S, pcm, rate, l_idx, r_idx)
     cores = oracle.max_threads() if threads <= 0 else threads
     streams = max(cores * 4, 8)
     batch = oracle.CpuBatch(streams, S, B, h)
@@ -157,11 +193,9 @@ def run_reference(args):
     desc, S, B, n_per_gpu, hrir = WORKLOADS[args.workload]
     pcm, rate = hrir_pcm_cpu(hrir)
     l_idx, r_idx = hesuvi14_cpu(S)
-    taps = pcm.shape[1]
+    h = cpu_filters(S, pcm, rate, l_idx, r_idx)
+    taps = h.shape[2]
     P = -(-taps // B)
-    h = np.zeros((S, 2, taps), np.float32)
-    for s in range(S):
-        h[s, 0], h[s, 1] = pcm[l_idx[s]], pcm[r_idx[s]]
     cores = oracle.max_threads()
     streams = max(cores * 4, 8)
     batch = oracle.CpuBatch(streams, S, B, h)
@@ -188,7 +222,8 @@ def run_reference(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "speakers": S, "block": B, "partitions": P, "taps": taps,
                    "note": "reference algorithm (one ConvolutionEngine per speaker x ear, zvmul+zvadd passes) restated in C "
-                           "(oracle/airwave_oracle.c); the Swift/vDSP reference cannot run on Linux"},
+                           "(oracle/airwave_oracle.c); the Swift/vDSP reference cannot run on Linux"
+                           + ("; the EQ cascade is not part of the CPU sample" if args.workload == "C4" else "")},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,8 +242,9 @@ def hrir_pcm_cpu(name: str):
         pcm = (0.05 * rng.standard_normal((14, 65536)) * np.exp(-n / (0.25 * FS))).astype(np.float32)
         pcm[:, 190] += 0.5
         return pcm, FS
+    name, _, relabel = name.partition("@")
     w = oracle.load_wav(os.path.join(GOLDEN, "hrtf", name + ".wav"))
-    return w.audioData, w.sampleRate
+    return w.audioData, (float(relabel) if relabel else w.sampleRate)
 
 
 def hesuvi14_cpu(S: int):
@@ -245,6 +281,11 @@ def run_ours(args):
     e2e_frames = max(B, min(4096, args.e2e_frames // B * B))
     eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=e2e_frames, max_partitions=P, device=local, pipelined=True)
     eng.set_bank(bank)
+    eq_def = eq_definition_for(args.workload, aw.EqualizerAPOParser.parse)
+    eq_filters = 0
+    if eq_def is not None:                    # full chain: spatial -> EQ (AudioEffectGraph.swift:195-210)
+        eng.eq_prepare(eq_def)
+        eq_filters = sum(1 for f in eq_def["filters"] if f.get("isEnabled", True))
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
 
     # device-resident synthetic input: a time-contiguous ring of R blocks per (stream, speaker)
@@ -296,16 +337,19 @@ def run_ours(args):
     prof = eng.profile_end()
     peak, peak_src = measured_peaks()
     plan = eng.plan()
-    step_bytes = n * algorithmic_bytes(S, B, P)
+    step_bytes = n * algorithmic_bytes(S, B, P, eq_filters)
     step_ms = elapsed_ms_max / K
     kernels_ms = {k: v["ms"] / max(v["launches"], 1) for k, v in prof.items()}
-    if plan["fused_tile"] > 0:
+    if len(plan["kernels"]) == 1:
         # one kernel does the whole block (K2+K3+K4): its algorithmic bytes are SURVEY.md 8(d)'s per-stream figure x streams
-        dom_name, dom_ms, dom_bytes = "k_fused", kernels_ms["fused"], step_bytes
+        dom_name = plan["kernels"][0]
+        dom_ms, dom_bytes = kernels_ms[dom_name], n * algorithmic_bytes(S, B, P)
     else:
-        dom_name, dom_ms = "k_fdl_cmac", kernels_ms["fdl_cmac"]
+        dom_name = plan["kernels"][1]
+        dom_ms = kernels_ms[dom_name]
         dom_bytes = n * (8 * S * B * P + 16 * B)      # FDL slots read once (P per speaker) + acc written
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    traffic = recorded_traffic(args.workload, dom_name)
     # end-to-end: pinned host buffers, every step's input H2D and output D2H inside the timed region
     F = e2e_frames
     n_bufs = 3
@@ -338,7 +382,9 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample = cpu_sample(S, B, pcm if rate == FS else pcm, l_idx, r_idx, args.cpu_seconds)
+        v, cores, sample = cpu_sample(S, B, pcm, rate, l_idx, r_idx, args.cpu_seconds)
+        if eq_def is not None:
+            sample += "; convolution only (the EQ cascade is not part of the CPU sample)"
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
@@ -347,11 +393,12 @@ def run_ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "streams_per_gpu": n, "speakers": S, "block": B, "partitions": P,
-                       "taps": taps, "step": f"one {B}-frame block for all streams (forward FFT -> FDL multiply-accumulate -> inverse FFT)",
+                       "taps": taps, "step": f"one {B}-frame block for all streams (forward FFT -> FDL multiply-accumulate -> inverse FFT"
+                               + (f" -> {eq_filters}-biquad float64 EQ cascade)" if eq_filters else ")"),
                        "l2": f"inputs larger than L2: the FDL working set read every step is {n * 8 * S * B * P / 1e6:.0f} MB (L2 = 126 MB)",
                        "plan": plan},
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                               "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "kernels_ms": kernels_ms},

@@ -228,8 +228,10 @@ AW_API int aw_engine_plan(const aw_engine *engine, int *fused_tile, int *mac_til
  * (K2 input_rfft, K3 fdl_cmac, K4 irfft_out) of up to `max_blocks` blocks on the engine's stream.  end() synchronises and
  * returns the summed milliseconds and launch counts per kernel (index 0..2); with the fused kernel index 0 is the whole
  * fused launch and 1..2 are zero.  Not for the real-time path. */
-AW_API int aw_engine_profile_begin(aw_engine *engine, int max_blocks);
+AW_API int aw_engine_profile_begin(aw_engine *engine, int max_blocks);   /* kernel_ms / kernel_launches below: 4 entries, [3] = equalizer */
 AW_API int aw_engine_profile_end(aw_engine *engine, double *kernel_ms, unsigned long long *kernel_launches);
+/* Comma-separated names of the kernels the engine launches per block, in launch order (e.g. "k_persistent<8,4>"). */
+AW_API int aw_engine_kernels(const aw_engine *engine, char *names, int capacity);
 /* Raw CUDA stream (cudaStream_t) the engine launches on, for event timing by the caller. */
 AW_API void *aw_engine_stream(const aw_engine *engine);
 /* Pinned host memory helpers for callers that cannot call cudaHostAlloc themselves. */

@@ -1,0 +1,246 @@
+"""GPU parity at BASELINE.json's full sizes, and agreement between the execution paths, through the C ABI.
+
+At 4,096 / 8,192 / 1,024 / 2,048 streams an element-wise CPU comparison of every stream is too slow for the oracle, so
+the tests use a size-independent property the domain offers — streams are independent and the engine is deterministic —
+on top of the oracle: the batch carries U distinct input signals repeated over all streams (so every tile of every
+persistent CTA sees all of them at every position inside a tile), the U distinct outputs are checked against the float64
+direct-convolution oracle (max-abs 1e-5, SNR >= 100 dB: BASELINE.json north_star), and every other stream must be
+BIT-IDENTICAL to its twin.  A stream whose rows were mixed up with a neighbour's, a tile that was skipped or processed
+twice, a ring slot that was read one block early — all of these break either the oracle check or the twin check.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import GOLDEN, snr_db
+
+pytestmark = pytest.mark.gpu
+
+MAX_ABS = 1e-5
+SNR_DB = 100.0
+SEED = 0x41495257
+FS = 48000.0
+
+
+@pytest.fixture(scope="module")
+def aw():
+    import airwave_b200
+    assert airwave_b200.device_count() > 0, "no CUDA device: the product has no CPU fallback"
+    return airwave_b200
+
+
+def _maps(aw, layout):
+    m = aw.HRIRChannelMap.hesuvi14Channel(layout.channels)
+    return [m.getIndices(s)[0] for s in layout.channels], [m.getIndices(s)[1] for s in layout.channels]
+
+
+def _render_twins(aw, bank, n, S, B, blocks, unique, per_call, pcm_lr, eq=None, env=None):
+    """Renders n streams carrying `unique` distinct signals (stream i carries signal i % unique); returns (x_unique, y)."""
+    old = {}
+    for k, v in (env or {}).items():
+        old[k] = os.environ.get(k)
+        os.environ[k] = v
+    try:
+        eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=per_call, max_partitions=bank.partitions)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    eng.set_bank(bank)
+    if eq is not None:
+        eng.eq_prepare(eq)
+    frames = blocks * B
+    xu = oracle.synth_block(SEED, [101 + 7 * i for i in range(unique)], S, 0, frames)
+    reps = -(-n // unique)
+    outs = []
+    for a in range(0, frames, per_call):
+        chunk = np.tile(xu[:, :, a:a + per_call], (reps, 1, 1))[:n]
+        outs.append(eng.process(np.ascontiguousarray(chunk)))
+    y = np.concatenate(outs, axis=2)
+    plan = eng.plan()
+    eng.close()
+    return xu, y, plan
+
+
+def _check_twins_and_oracle(xu, y, h, unique, eq_definition=None):
+    n = y.shape[0]
+    for i in range(unique, n):                       # every stream is bit-identical to its twin among the first `unique`
+        assert np.array_equal(y[i], y[i % unique]), f"stream {i} differs from its twin {i % unique}"
+    for i in range(unique):
+        ref = oracle.direct_conv_f64(xu[i], h)
+        if eq_definition is not None:
+            # float64 convolution narrowed to Float (RealtimeAudioProcessor output), then the reference's Double biquad cascade
+            o = oracle.ParametricEqualizerProcessor(FS)
+            o.setTarget(eq_definition)
+            l, r = [], []
+            for a in range(0, ref.shape[1], 4096):
+                ll, rr = o.process(ref[0, a:a + 4096].astype(np.float32), ref[1, a:a + 4096].astype(np.float32))
+                l.append(ll); r.append(rr)
+            ref = np.stack([np.concatenate(l), np.concatenate(r)]).astype(np.float64)
+        assert np.abs(y[i] - ref).max() <= MAX_ABS, i
+        assert snr_db(ref, y[i]) >= SNR_DB, i
+
+
+def test_c2_full_size_4096_streams(aw, hrtf_path):
+    """BASELINE configs[1]: 7.1 -> binaural, RoomSH1.0, B = 256, 4,096 concurrent streams on one GPU."""
+    lay = aw.InputLayout.surround71()
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), FS, lay, 256)
+    xu, y, plan = _render_twins(aw, bank, 4096, 8, 256, blocks=24, unique=12, per_call=1024, pcm_lr=None)
+    assert plan["kernels"] == ["k_persistent<8,4>"]
+    h = oracle.hrir_matrix(oracle.load_wav(hrtf_path("RoomSH1.0")), FS, oracle.InputLayout.surround71)
+    _check_twins_and_oracle(xu, y, h, 12)
+
+
+def test_c4_full_chain_8192_streams(aw, hrtf_path, eq_fixture_bytes):
+    """BASELINE configs[3]: 7.1 HRIR convolution + 10-band parametric EQ + HRIR 44.1 -> 48 kHz resample, 8,192 streams.
+    The bundled presets are 48 kHz files, so the 44.1 kHz source is StageSH1.0 relabelled."""
+    lay = aw.InputLayout.surround71()
+    wav_o = oracle.load_wav(hrtf_path("StageSH1.0"))
+    l, r = _maps(aw, lay)
+    bank = aw.HRIRBank(wav_o.audioData, 44100.0, FS, l, r, 256)
+    assert (bank.taps, bank.partitions) == (4702, 19)
+    definition = aw.EqualizerAPOParser.parse(eq_fixture_bytes, "CCA CRA ParametricEq.txt")
+    assert len(definition["filters"]) == 10
+    # installing the state directly (no 20 ms crossfade from unity) keeps the reference chain simple: conv -> cascade
+    old = None
+    n, unique = 8192, 10
+    eng = aw.BinauralEngine(n, 8, 256, FS, max_frames_per_call=1024, max_partitions=19)
+    eng.set_bank(bank)
+    eng.eq_install_state(definition)
+    frames = 24 * 256
+    xu = oracle.synth_block(SEED, [3 + 5 * i for i in range(unique)], 8, 0, frames)
+    reps = -(-n // unique)
+    y = np.concatenate([eng.process(np.ascontiguousarray(np.tile(xu[:, :, a:a + 1024], (reps, 1, 1))[:n]))
+                        for a in range(0, frames, 1024)], axis=2)
+    assert eng.plan()["kernels"] == ["k_persistent<8,4>"]
+    eng.close()
+    wav_o.sampleRate = 44100.0
+    h = oracle.hrir_matrix(wav_o, FS, oracle.InputLayout.surround71)
+    assert h.shape[2] == 4702
+    for i in range(unique, n):
+        assert np.array_equal(y[i], y[i % unique]), i
+    for i in range(unique):
+        conv = oracle.direct_conv_f64(xu[i], h)
+        st = oracle.ParametricEqualizerState(definition, FS)
+        el, er = st.process(conv[0].astype(np.float32), conv[1].astype(np.float32))
+        ref = np.stack([el, er]).astype(np.float64)
+        # the EQ's peaking gains amplify the convolution's float32 rounding: compare at the EQ's own scale
+        scale = max(1.0, float(np.abs(ref).max() / max(np.abs(conv).max(), 1e-30)))
+        assert np.abs(y[i] - ref).max() <= MAX_ABS * scale, i
+        assert snr_db(ref, y[i]) >= SNR_DB - 6.0, i
+
+
+def test_c3_full_size_1024_streams_long_brir(aw):
+    """BASELINE configs[2]: synthetic 65,536-tap BRIR, P = 128 at B = 512, 1,024 streams; more than P blocks so every
+    stream's ring wraps (Q4)."""
+    from scipy.signal import fftconvolve
+    rng = np.random.default_rng(1)
+    taps, B, S = 65536, 512, 8
+    t = np.arange(taps)
+    pcm = (0.05 * rng.standard_normal((14, taps)) * np.exp(-t / (0.25 * FS))).astype(np.float32)
+    pcm[:, 190] += 0.5
+    lay = aw.InputLayout.surround71()
+    l, r = _maps(aw, lay)
+    bank = aw.HRIRBank(pcm, FS, FS, l, r, B)
+    assert bank.partitions == 128
+    unique, blocks = 3, 132
+    xu, y, plan = _render_twins(aw, bank, 1024, S, B, blocks=blocks, unique=unique, per_call=4096, pcm_lr=None)
+    assert plan["kernels"][0].startswith("k_persistent<9,")
+    for i in range(unique, 1024):
+        assert np.array_equal(y[i], y[i % unique]), i
+    for i in range(unique):
+        ref = np.zeros((2, blocks * B))
+        for s in range(S):
+            ref[0] += fftconvolve(xu[i, s].astype(np.float64), pcm[l[s]].astype(np.float64))[: blocks * B]
+            ref[1] += fftconvolve(xu[i, s].astype(np.float64), pcm[r[s]].astype(np.float64))[: blocks * B]
+        assert np.abs(y[i] - ref).max() <= MAX_ABS, i
+        assert snr_db(ref, y[i]) >= SNR_DB, i
+
+
+@pytest.mark.parametrize("block", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_c5_block_size_sweep_2048_streams(aw, hrtf_path, block):
+    """BASELINE configs[4] per GPU: 2,048 streams, block sizes 64 ... 4096 (P = 68 ... 2)."""
+    lay = aw.InputLayout.surround71()
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), FS, lay, block)
+    P = -(-4320 // block)
+    assert bank.partitions == P
+    blocks = max(3, min(P + 3, 4 * 4096 // block))
+    per_call = min(4096, 4 * block)
+    xu, y, plan = _render_twins(aw, bank, 2048, 8, block, blocks=blocks, unique=6, per_call=per_call, pcm_lr=None)
+    if 64 <= block <= 2048:
+        assert plan["kernels"][0].startswith("k_persistent<"), plan
+    h = oracle.hrir_matrix(oracle.load_wav(hrtf_path("RoomSH1.0")), FS, oracle.InputLayout.surround71)
+    _check_twins_and_oracle(xu, y, h, 6)
+
+
+PATHS = [  # (name, env, block sizes it exists for)
+    ("persistent T=4", {"AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512, 1024)),
+    ("persistent T=2", {"AW_PERSISTENT_TILE": "2"}, (64, 128, 256, 512, 1024, 2048)),
+    ("persistent, 3 CTAs", {"AW_PERSISTENT_CTAS": "3"}, (64, 256, 2048)),
+    ("fused", {"AW_PERSISTENT": "0"}, (64, 128, 256, 512)),
+    ("split", {"AW_FUSED_TILE": "0"}, (64, 128, 256, 512, 1024, 2048)),
+]
+
+
+@pytest.mark.parametrize("block", [64, 128, 256, 512, 1024, 2048])
+def test_execution_paths_agree(aw, hrtf_path, block):
+    """KP (both tile sizes, few CTAs so that every CTA walks many tiles), KF and the split kernels K2/K3/K4 compute the same
+    convolution; they differ only in summation order, so they agree to float32 rounding and each meets the oracle bound.
+    Odd stream counts exercise the partial last tile."""
+    lay = aw.InputLayout.surround71()
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("StageSH1.0")), FS, lay, block)
+    P = bank.partitions
+    blocks = max(3, min(P + 2, 40))
+    n = 23
+    h = oracle.hrir_matrix(oracle.load_wav(hrtf_path("StageSH1.0")), FS, oracle.InputLayout.surround71)
+    results = {}
+    for name, env, sizes in PATHS:
+        if block not in sizes:
+            continue
+        xu, y, plan = _render_twins(aw, bank, n, 8, block, blocks=blocks, unique=n, per_call=min(4096, 2 * block), pcm_lr=None, env=env)
+        results[name] = (y, plan["kernels"])
+        for i in (0, 10, 22):
+            ref = oracle.direct_conv_f64(xu[i], h)
+            assert np.abs(y[i] - ref).max() <= MAX_ABS, (name, i)
+            assert snr_db(ref, y[i]) >= SNR_DB, (name, i)
+    kernels = {name: k for name, (_, k) in results.items()}
+    assert kernels["split"][1].startswith("k_fdl_cmac"), kernels
+    if "fused" in kernels:
+        assert kernels["fused"][0].startswith("k_fused<"), kernels
+    base = results["persistent T=2"][0]
+    if "persistent T=4" in results:   # the tile size must not change a single bit (multi-GPU sharding relies on it)
+        assert np.array_equal(results["persistent T=4"][0], base)
+    if "persistent, 3 CTAs" in results:
+        assert np.array_equal(results["persistent, 3 CTAs"][0], base)
+    for name, (y, _) in results.items():
+        assert np.abs(y - base).max() <= 4e-6, name
+
+
+def test_small_and_ragged_stream_counts_and_stereo_on_the_persistent_path(aw, hrtf_path):
+    """n = 1, 2, 5 (partial tiles), S = 2 (bank narrower than a stage row group) and P = 1 (heads only)."""
+    wav_o = oracle.load_wav(hrtf_path("NeutralSH1.0"))
+    for layout, S, n, block in [("stereo", 2, 1, 512), ("stereo", 2, 5, 64), ("surround51", 6, 2, 128), ("surround71", 8, 5, 1024)]:
+        lay = getattr(aw.InputLayout, layout)()
+        bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("NeutralSH1.0")), FS, lay, block)
+        blocks = bank.partitions + 2
+        xu, y, plan = _render_twins(aw, bank, n, S, block, blocks=blocks, unique=n, per_call=block, pcm_lr=None)
+        assert plan["kernels"][0].startswith("k_persistent<"), plan
+        h = oracle.hrir_matrix(wav_o, FS, getattr(oracle.InputLayout, layout))
+        for i in range(n):
+            ref = oracle.direct_conv_f64(xu[i], h)
+            assert np.abs(y[i] - ref).max() <= MAX_ABS and snr_db(ref, y[i]) >= SNR_DB, (layout, n, block, i)
+    # P = 1: a 200-tap response in one 256-frame partition
+    lay = aw.InputLayout.stereo()
+    l, r = _maps(aw, lay)
+    short = wav_o.audioData[:, :200].copy()
+    bank = aw.HRIRBank(short, FS, FS, l, r, 256)
+    assert bank.partitions == 1
+    xu, y, plan = _render_twins(aw, bank, 9, 2, 256, blocks=5, unique=9, per_call=256, pcm_lr=None)
+    hs = np.stack([np.stack([short[l[s]], short[r[s]]]) for s in range(2)])
+    for i in range(9):
+        ref = oracle.direct_conv_f64(xu[i], hs)
+        assert np.abs(y[i] - ref).max() <= MAX_ABS, i
