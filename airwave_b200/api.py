@@ -342,7 +342,7 @@ class BinauralEngine:
         """Names of the kernels launched per block, in launch order (e.g. ['k_persistent<8,4>'])."""
         buf = C.create_string_buffer(256)
         L.check(L.lib().aw_engine_kernels(self._h, buf, 256))
-        return buf.value.decode().split(",")
+        return buf.value.decode().split(";")
 
     def profile_begin(self, max_blocks: int) -> None:
         L.check(L.lib().aw_engine_profile_begin(self._h, max_blocks))

@@ -1253,7 +1253,7 @@ extern "C" int aw_engine_kernels(const aw_engine *e, char *names, int capacity)
     std::string n;
     if (e->persistent) n = "k_persistent<" + std::to_string(lb) + "," + std::to_string(e->persistentTile) + ">";
     else if (e->fusedTile > 0) n = "k_fused<" + std::to_string(lb) + "," + std::to_string(e->fusedTile) + ">";
-    else n = "k_input_rfft<" + std::to_string(lb) + ">,k_fdl_cmac<" + std::to_string(e->macTile) + ">,k_irfft_out<" + std::to_string(lb) + ">";
+    else n = "k_input_rfft<" + std::to_string(lb) + ">;k_fdl_cmac<" + std::to_string(e->macTile) + ">;k_irfft_out<" + std::to_string(lb) + ">";
     if ((int)n.size() + 1 > capacity) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_kernels: capacity too small");
     memcpy(names, n.c_str(), n.size() + 1);
     return AW_OK;

@@ -5,23 +5,29 @@
 // 146-163): forward real FFT of the T*S overlap-save frames, frequency-domain delay-line multiply-accumulate over all
 // (speaker, partition) pairs for both ears, inverse real FFT with the overlap-save discard.
 //
-//   warp 0 (producer)   streams FDL rows and the matching filter rows into a deep shared-memory ring with TMA-class
-//                       bulk copies (cp.async.bulk ... mbarrier::complete_tx); every lane issues one copy of a stage, so
-//                       a stage of up to 20 copies costs one instruction slot.  A stage holds R (speaker, partition)
-//                       pairs x C bin pairs for the T streams: C = min(B/2, 128) and R = 128/C, i.e. always 128 bin-pair
-//                       lanes of work per stream group whatever the block size.  Rows wider than 128 bin pairs are walked
-//                       in column chunks (accumulators stay in registers for the whole chunk).
-//   8 MAC warps         two groups of 128 threads, T/2 streams each; a thread owns one bin pair (two complex bins, one
-//                       float4 of FDL) of one row of the stage, both ears.  full/empty mbarriers per stage.  With R > 1
-//                       the R partial sums are reduced through shared memory in a fixed order (deterministic).
+//   4 producer warps    one elected lane each; producer w issues the stages k = w, w+4, ... of this CTA's stage sequence:
+//                       FDL rows and the matching filter rows go into a deep shared-memory ring with TMA-class bulk copies
+//                       (cp.async.bulk ... mbarrier::complete_tx).  (UBLKCP takes uniform operands, so lane-parallel issue
+//                       would be serialised by the compiler; independent warps really do issue in parallel.)  A stage holds
+//                       R consecutive partitions of one speaker x C bin pairs for the T streams: C = min(B/2, 128) and
+//                       R = 128/C, i.e. always 128 bin-pair lanes of work per stream group whatever the block size; the
+//                       R FDL rows of a stream are consecutive ring slots, so they travel as one copy (two at the wrap).
+//                       Rows wider than 128 bin pairs are walked in column chunks (accumulators stay in registers for the
+//                       whole chunk).
+//   8 MAC warps         two sets of 128 threads that take alternate stages; a thread owns one bin pair (two complex bins, one
+//                       float4 of FDL) of one row of the stage for ALL T streams and both ears, so a filter value is read
+//                       from shared memory once per T streams (shared-memory bandwidth is the resource next to HBM here).
+//                       full/empty mbarriers per stage.  The partial sums of the sets (and of the R rows) are reduced
+//                       through shared memory in a fixed order (deterministic).
 //   4 or 8 FFT warps    run the forward transforms ONE TILE AHEAD of the MAC warps (nothing but the head slot of the FDL
 //                       depends on them), and the inverse transforms of the tile the MAC warps just finished
 //                       (accumulators handed over through shared memory, acc_ready/acc_free mbarriers).
 //
 // The head partition (p = 0) is streamed like any other row: the FFT warps publish it with a generic->async proxy fence
 // + the head_ready mbarrier, which the producer waits on before it issues the first head row of a tile.
-// Pair order inside a tile: all (s, p >= 1) pairs speaker-major, then the S head pairs — the same for every tile size and
-// stream count, so a stream's output does not depend on how many streams the engine renders or on which GPU it lives.
+// Stage order inside a tile (and column chunk): for every speaker its history partitions p = 1..P-1 in groups of R, then
+// the S head rows — the same for every tile size and stream count, so a stream's output does not depend on how many
+// streams the engine renders or on which GPU it lives.
 #include "aw_fft_blocks.cuh"
 
 namespace aw {
@@ -32,26 +38,27 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int C = halfB < 128 ? halfB : 128;      // bin pairs per column chunk
     static constexpr int NC = halfB / C;                     // column chunks per row
     static constexpr int R = 128 / C;                        // (speaker, partition) pairs per stage
-    static constexpr int MAC_GROUPS = 2, TG = T / MAC_GROUPS;
-    static constexpr int MAC_THREADS = MAC_GROUPS * 128;
+    static constexpr int MAC_SETS = 2;                       // sets of 128 MAC threads; set q consumes the stages k = q (mod 2)
+    static constexpr int MAC_THREADS = MAC_SETS * 128;
     static constexpr int G = RegFft<LOG2M>::G;               // threads per transform
     static constexpr int FFT_THREADS = 8 * G <= 128 ? 128 : 256;
     static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
-    static constexpr int THREADS = 32 + MAC_THREADS + FFT_THREADS;
+    static constexpr int PRODUCERS = 4;                      // producer warps, one issuing lane each
+    static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
     static constexpr int PS = PaddedSize<LOG2M>::value;
-    static constexpr int stage_f4 = R * (T + 2) * C;         // R x (T FDL rows + 2 filter planes) x C float4
+    static constexpr int stage_f4 = R * (T + 2) * C;         // FDL [T][R][C] + filter [R][2 planes][C] float4
     static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
-    static constexpr int CPR = T + (NC == 1 ? 1 : 2);        // bulk copies per pair
-    static constexpr int red_f4 = (R - 1) * T * 2 * C;       // partial sums of rows 1..R-1
+    static constexpr int red_f4 = (MAC_SETS * R - 1) * T * 2 * C;   // partial sums of every (set, row) but the first
     static constexpr size_t fixed_bytes = (size_t)M * sizeof(float2)                    // twiddles
                                           + (size_t)(NFT + 2 * T) * PS * sizeof(float2)  // forward buffers + accumulator buffers
                                           + (size_t)red_f4 * sizeof(float4) + (size_t)FFT_THREADS * sizeof(float) + 1024;
     static constexpr int max_stages = (int)((226 * 1024 - fixed_bytes) / stage_bytes);
-    static constexpr int STAGES = max_stages > 32 ? 32 : max_stages;
+    // A ring slot must always be filled by the same producer warp and drained by the same MAC set (mbarrier parity waits are
+    // only safe for a waiter that is at most one phase behind), hence a multiple of PRODUCERS (and of MAC_SETS).
+    static constexpr int STAGES = (max_stages > 32 ? 32 : max_stages) / PRODUCERS * PRODUCERS;
     static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
     static constexpr bool PREFETCH = LOG2M <= 8;             // next round's operands fetched while this round transforms
-    static_assert(R * CPR <= 32, "one lane per bulk copy");
-    static_assert(STAGES >= 4, "ring too shallow");
+    static_assert(STAGES >= 4 && STAGES % PRODUCERS == 0 && STAGES % MAC_SETS == 0, "ring geometry");
 };
 
 struct PersistArgs {
@@ -67,21 +74,13 @@ struct PersistArgs {
     int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms
 };
 
-// (speaker, partition) of pair `idx`: history pairs first (speaker-major, p = 1..P-1), then the S head pairs.
-__device__ __forceinline__ void pair_sp(int idx, int S, int P, int &s, int &p)
-{
-    const int hist = S * (P - 1);
-    if (idx < hist) { s = idx / (P - 1); p = 1 + idx - s * (P - 1); }
-    else { s = idx - hist; p = 0; }
-}
-
 template <int LOG2M, int T>
 __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const PersistArgs a)
 {
     using PG = PGeo<LOG2M, T>;
-    constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, TG = PG::TG, G = PG::G, NFT = PG::NFT;
-    constexpr int STAGES = PG::STAGES, PS = PG::PS, stage_f4 = PG::stage_f4, CPR = PG::CPR;
-    constexpr int MAC_WARPS = PG::MAC_THREADS / 32, FFT_WARPS = PG::FFT_THREADS / 32;
+    constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, G = PG::G, NFT = PG::NFT;
+    constexpr int STAGES = PG::STAGES, PS = PG::PS, stage_f4 = PG::stage_f4, PRODUCERS = PG::PRODUCERS;
+    constexpr int MAC_WARPS = PG::MAC_THREADS / 32, SET_WARPS = 4, FFT_WARPS = PG::FFT_THREADS / 32;
     constexpr int BAR_RED_A = 1, BAR_RED_B = 2, BAR_FFT0 = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *ring = reinterpret_cast<float4 *>(smem_raw);
@@ -101,13 +100,11 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     const int n_tiles = (g.n_streams + T - 1) / T;
     const int last = g.first_stream + g.n_streams - 1;
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int n_pairs = g.S * g.P;
-    const int spc = (n_pairs + R - 1) / R;               // stages per column chunk
-    const int head_stage = g.S * (g.P - 1) / R;          // first stage of a chunk that holds a head pair
+    const int hs = (g.P - 1 + R - 1) / R;                // history stages per speaker (groups of R partitions)
 
     for (int k = tid; k < M; k += PG::THREADS) tw[k] = a.tw[k];
     if (tid == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], MAC_WARPS); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], SET_WARPS); }
         mbar_init(&head_ready[0], FFT_WARPS);
         mbar_init(&head_ready[1], FFT_WARPS);
         mbar_init(acc_ready, MAC_WARPS);
@@ -116,113 +113,128 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     }
     __syncthreads();
 
-    if (warp == 0) {
-        // ===== producer =====
-        const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
-        const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
-        int stage = 0;
-        unsigned phase = 0;
-        for (int lt = 0; lt < my_tiles; ++lt) {
-            const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
-            for (int c = 0; c < NC; ++c) {
-                for (int j = 0; j < spc; ++j) {
-                    if (c == 0 && j == head_stage) mbar_wait(&head_ready[lt & 1], (unsigned)((lt >> 1) & 1));
-                    if (lane == 0) mbar_wait(&empty[stage], phase ^ 1u);
-                    __syncwarp();
-                    const int nrows = min(R, n_pairs - j * R);
-                    if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)(nrows * (T + 2) * C * sizeof(float4)));
-                    __syncwarp();
-                    if (lane < nrows * CPR) {
-                        const int r = lane / CPR, q = lane - r * CPR;
-                        int s, p;
-                        pair_sp(j * R + r, g.S, g.P, s, p);
-                        int slot = g.head + p;
-                        if (slot >= g.P) slot -= g.P;                  // modulus is partitionCount (Q4)
-                        float4 *dst = ring + (size_t)stage * stage_f4;
-                        if (q < T) {
-                            bulk_g2s(dst + (r * T + q) * C,
-                                     fdl4 + (size_t)min(s0 + q, last) * stream_stride + ((size_t)s * g.P_cap + slot) * halfB + c * C,
-                                     (unsigned)(C * sizeof(float4)), &full[stage]);
-                        } else if (NC == 1) {                          // both planes of the filter row are contiguous
-                            bulk_g2s(dst + R * T * C + r * 2 * C, a.bank + ((size_t)s * g.P + p) * M, (unsigned)(2 * C * sizeof(float4)),
-                                     &full[stage]);
-                        } else {
-                            const int pl = q - T;
-                            bulk_g2s(dst + R * T * C + (r * 2 + pl) * C, a.bank + ((size_t)s * g.P + p) * M + pl * halfB + c * C,
-                                     (unsigned)(C * sizeof(float4)), &full[stage]);
-                        }
-                    }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+    if (warp < PRODUCERS) {
+        // ===== producers: warp w issues the stages k = w, w + PRODUCERS, ... of this CTA's stage sequence =====
+        if (lane == 0) {
+            const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+            const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
+            // position of this producer in the stage sequence, advanced one stage at a time (no divisions on the issue path):
+            // tile lt, column chunk c, and inside the chunk either history group jj of speaker s or the head row of speaker s
+            int lt = 0, c = 0, s = 0, jj = 0, stage = 0;
+            unsigned phase = 0;
+            bool hist = hs > 0;
+            auto advance = [&]() {
+                if (hist) {
+                    if (++jj == hs) { jj = 0; if (++s == g.S) { s = 0; hist = false; } }
+                } else if (++s == g.S) {
+                    s = 0; hist = hs > 0;
+                    if (++c == NC) { c = 0; ++lt; }
                 }
+                if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            };
+            for (int i = 0; i < warp; ++i) advance();
+            int waited = -1;                                 // head_ready phases observed so far (tiles 0..waited)
+            while (lt < my_tiles) {
+                const int p0 = hist ? 1 + jj * R : 0;
+                const int nrows = hist ? min(R, g.P - p0) : 1;
+                // head rows of tile lt exist once the FFT warps have published them; phases are observed strictly in order
+                const int need = (c > 0 || !hist) ? lt : lt - 1;
+                while (waited < need) { ++waited; mbar_wait(&head_ready[waited & 1], (unsigned)((waited >> 1) & 1)); }
+                const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
+                int slot = g.head + p0;
+                if (slot >= g.P) slot -= g.P;                // modulus is partitionCount (Q4)
+                const int n1 = min(nrows, g.P - slot);       // rows before the ring wraps
+                mbar_wait(&empty[stage], phase ^ 1u);
+                mbar_expect_tx(&full[stage], (unsigned)(nrows * (T + 2) * C * sizeof(float4)));
+                float4 *dst = ring + (size_t)stage * stage_f4;
+#pragma unroll
+                for (int u = 0; u < T; ++u) {
+                    const float4 *row = fdl4 + (size_t)min(s0 + u, last) * stream_stride + (size_t)s * g.P_cap * halfB + c * C;
+                    bulk_g2s(dst + (u * R) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage]);
+                    if (R > 1 && n1 < nrows)
+                        bulk_g2s(dst + (u * R + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage]);
+                }
+                const float4 *frow = a.bank + ((size_t)s * g.P + p0) * M;
+                if (NC == 1) {                               // whole rows: both planes of R consecutive partitions are contiguous
+                    bulk_g2s(dst + T * R * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage]);
+                } else {
+                    bulk_g2s(dst + T * C, frow + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
+                    bulk_g2s(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
+                }
+#pragma unroll
+                for (int i = 0; i < PRODUCERS; ++i) advance();
             }
         }
-    } else if (warp < 1 + MAC_WARPS) {
-        // ===== MAC warps =====
-        const int mt = tid - 32;
-        const int gi = mt >> 7, w = mt & 127;
+    } else if (warp < PRODUCERS + MAC_WARPS) {
+        // ===== MAC warps: set q consumes the stages k = q (mod 2); a thread owns one bin pair of one row, all T streams =====
+        const int mt = tid - 32 * PRODUCERS;
+        const int set = mt >> 7, w = mt & 127;
         const int r = w / C, jp = w - r * C;
-        int stage = 0;
+        const int contributor = set * R + r;                 // partial sums are reduced in this order
+        int stage = 0, turn = 0;
         unsigned phase = 0;
         for (int lt = 0; lt < my_tiles; ++lt) {
             for (int c = 0; c < NC; ++c) {
-                float4 aL[TG], aR[TG];
+                float4 aL[T], aR[T];
 #pragma unroll
-                for (int u = 0; u < TG; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
-                for (int j = 0; j < spc; ++j) {
-                    mbar_wait(&full[stage], phase);
-                    if (r < n_pairs - j * R) {
-                        const float4 *src = ring + (size_t)stage * stage_f4;
-                        const float4 h0 = src[R * T * C + (r * 2) * C + jp], h1 = src[R * T * C + (r * 2 + 1) * C + jp];
-                        float4 x[TG];
+                for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
+                auto consume = [&](int nrows) {
+                    if (turn == set) {
+                        mbar_wait(&full[stage], phase);
+                        if (r < nrows) {
+                            const float4 *src = ring + stage * stage_f4;
+                            const float4 h0 = src[T * R * C + (r * 2) * C + jp], h1 = src[T * R * C + (r * 2 + 1) * C + jp];
+                            float4 x[T];
 #pragma unroll
-                        for (int u = 0; u < TG; ++u) x[u] = src[(r * T + gi * TG + u) * C + jp];
+                            for (int u = 0; u < T; ++u) x[u] = src[(u * R + r) * C + jp];
 #pragma unroll
-                        for (int u = 0; u < TG; ++u) {
-                            cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
-                            cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&empty[stage]);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                }
-                // the FFT warps must be done with the previous tile's accumulators before they are overwritten
-                if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
-                if constexpr (R > 1) {
-                    if (r > 0) {
-#pragma unroll
-                        for (int u = 0; u < TG; ++u) {
-                            float4 *d = red + ((size_t)(((r - 1) * PG::MAC_GROUPS + gi) * TG + u) * 2) * C + jp;
-                            d[0] = aL[u];
-                            d[C] = aR[u];
-                        }
-                    }
-                    named_sync(BAR_RED_A, PG::MAC_THREADS);
-                    if (r == 0) {
-#pragma unroll
-                        for (int rr = 1; rr < R; ++rr) {
-#pragma unroll
-                            for (int u = 0; u < TG; ++u) {
-                                const float4 *d = red + ((size_t)(((rr - 1) * PG::MAC_GROUPS + gi) * TG + u) * 2) * C + jp;
-                                const float4 l = d[0], rt = d[C];
-                                aL[u].x += l.x; aL[u].y += l.y; aL[u].z += l.z; aL[u].w += l.w;
-                                aR[u].x += rt.x; aR[u].y += rt.y; aR[u].z += rt.z; aR[u].w += rt.w;
+                            for (int u = 0; u < T; ++u) {
+                                cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
+                                cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
                             }
                         }
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty[stage]);
                     }
-                    named_sync(BAR_RED_B, PG::MAC_THREADS);
+                    turn ^= 1;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                };
+                for (int s = 0; s < g.S; ++s)
+                    for (int jj = 0; jj < hs; ++jj) consume(min(R, g.P - 1 - jj * R));
+                for (int s = 0; s < g.S; ++s) consume(1);
+                // the FFT warps must be done with the previous tile's accumulators before they are overwritten
+                if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
+                if (contributor > 0) {
+#pragma unroll
+                    for (int u = 0; u < T; ++u) {
+                        float4 *d = red + ((size_t)((contributor - 1) * T + u) * 2) * C + jp;
+                        d[0] = aL[u];
+                        d[C] = aR[u];
+                    }
                 }
-                if (r == 0) {
+                named_sync(BAR_RED_A, PG::MAC_THREADS);
+                if (contributor == 0) {
+#pragma unroll
+                    for (int q = 1; q < PG::MAC_SETS * R; ++q) {
+#pragma unroll
+                        for (int u = 0; u < T; ++u) {
+                            const float4 *d = red + ((size_t)((q - 1) * T + u) * 2) * C + jp;
+                            const float4 l = d[0], rt = d[C];
+                            aL[u].x += l.x; aL[u].y += l.y; aL[u].z += l.z; aL[u].w += l.w;
+                            aR[u].x += rt.x; aR[u].y += rt.y; aR[u].z += rt.z; aR[u].w += rt.w;
+                        }
+                    }
                     const int J = c * C + jp;   // bins 2J, 2J+1
 #pragma unroll
-                    for (int u = 0; u < TG; ++u) {
-                        float2 *bl = accbuf + (size_t)(2 * (gi * TG + u)) * PS, *br = bl + PS;
+                    for (int u = 0; u < T; ++u) {
+                        float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
                         bl[pad16(2 * J)] = make_float2(aL[u].x, aL[u].y);
                         bl[pad16(2 * J + 1)] = make_float2(aL[u].z, aL[u].w);
                         br[pad16(2 * J)] = make_float2(aR[u].x, aR[u].y);
                         br[pad16(2 * J + 1)] = make_float2(aR[u].z, aR[u].w);
                     }
                 }
+                named_sync(BAR_RED_B, PG::MAC_THREADS);      // the partial sums may be overwritten by the next chunk
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_ready);
@@ -230,7 +242,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     } else {
         // ===== FFT warps =====
         using F = RegFft<LOG2M>;
-        const int ft = tid - 32 - PG::MAC_THREADS;
+        const int ft = tid - 32 * PRODUCERS - PG::MAC_THREADS;
         const int f = ft / G, t = ft - f * G;
         const int warp_first_f = G >= 32 ? f : (ft - lane) / G;   // first transform handled by this warp
         const GroupBar gb{BAR_FFT0 + f, G};

@@ -230,7 +230,7 @@ AW_API int aw_engine_plan(const aw_engine *engine, int *fused_tile, int *mac_til
  * fused launch and 1..2 are zero.  Not for the real-time path. */
 AW_API int aw_engine_profile_begin(aw_engine *engine, int max_blocks);   /* kernel_ms / kernel_launches below: 4 entries, [3] = equalizer */
 AW_API int aw_engine_profile_end(aw_engine *engine, double *kernel_ms, unsigned long long *kernel_launches);
-/* Comma-separated names of the kernels the engine launches per block, in launch order (e.g. "k_persistent<8,4>"). */
+/* Semicolon-separated names of the kernels the engine launches per block, in launch order (e.g. "k_persistent<8,4>"). */
 AW_API int aw_engine_kernels(const aw_engine *engine, char *names, int capacity);
 /* Raw CUDA stream (cudaStream_t) the engine launches on, for event timing by the caller. */
 AW_API void *aw_engine_stream(const aw_engine *engine);

@@ -180,7 +180,8 @@ def test_c5_block_size_sweep_2048_streams(aw, hrtf_path, block):
 PATHS = [  # (name, env, block sizes it exists for)
     ("persistent T=4", {"AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512, 1024)),
     ("persistent T=2", {"AW_PERSISTENT_TILE": "2"}, (64, 128, 256, 512, 1024, 2048)),
-    ("persistent, 3 CTAs", {"AW_PERSISTENT_CTAS": "3"}, (64, 256, 2048)),
+    ("persistent T=2, 3 CTAs", {"AW_PERSISTENT_CTAS": "3", "AW_PERSISTENT_TILE": "2"}, (64, 128, 256, 512, 1024, 2048)),
+    ("persistent T=4, 2 CTAs", {"AW_PERSISTENT_CTAS": "2", "AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512, 1024)),
     ("fused", {"AW_PERSISTENT": "0"}, (64, 128, 256, 512)),
     ("split", {"AW_FUSED_TILE": "0"}, (64, 128, 256, 512, 1024, 2048)),
 ]
@@ -214,8 +215,9 @@ def test_execution_paths_agree(aw, hrtf_path, block):
     base = results["persistent T=2"][0]
     if "persistent T=4" in results:   # the tile size must not change a single bit (multi-GPU sharding relies on it)
         assert np.array_equal(results["persistent T=4"][0], base)
-    if "persistent, 3 CTAs" in results:
-        assert np.array_equal(results["persistent, 3 CTAs"][0], base)
+    for few in ("persistent T=2, 3 CTAs", "persistent T=4, 2 CTAs"):   # every CTA walks several tiles
+        if few in results:
+            assert np.array_equal(results[few][0], base), few
     for name, (y, _) in results.items():
         assert np.abs(y - base).max() <= 4e-6, name
 
