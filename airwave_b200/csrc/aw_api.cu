@@ -867,8 +867,10 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
                 const double tiles = (double)((e->n + T - 1) / T);
                 return (double)e->n / ((double)T * std::ceil(tiles / e->persistentCtas) * e->persistentCtas);
             };
-            e->persistentTile = (mask & 4) ? 4 : 2;
-            if ((mask & 4) && (mask & 2) && eff(2) > 1.08 * eff(4)) e->persistentTile = 2;
+            // measured (C5 sweep, 2,048 streams): T = 4 wins up to B = 512 even with a ragged last round, T = 2 from B = 1024
+            // (its ring is deeper there); tiny batches take T = 2 so that more SMs get a tile
+            e->persistentTile = (mask & 4) && e->log2m <= 9 ? 4 : 2;
+            if ((mask & 2) && (e->n + 3) / 4 < e->persistentCtas && eff(2) > eff(4)) e->persistentTile = 2;
             const char *t_env = getenv("AW_PERSISTENT_TILE");
             if (t_env && (atoi(t_env) & mask) && (atoi(t_env) == 2 || atoi(t_env) == 4)) e->persistentTile = atoi(t_env);
         }

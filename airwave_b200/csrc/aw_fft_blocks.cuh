@@ -217,23 +217,25 @@ __device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fd
 {
     float sum = 0.f;
     if (active) {
-        const int terms = g.S * g.P;
-        for (int i0 = t; i0 < terms; i0 += 8 * G) {     // 8 independent load pairs in flight per thread
-            float xa[8], ha[8];
+        for (int s = 0; s < g.S; ++s) {
+            const float *xrow = fdl_ny + ((size_t)stream * g.Se + s) * g.P_cap;
+            const float *hrow = bank_ny + (size_t)s * g.P * 2 + ear;
+            for (int p0 = t; p0 < g.P; p0 += 8 * G) {     // 8 independent load pairs in flight per thread
+                float xa[8], ha[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int i = i0 + k * G;
-                xa[k] = 0.f; ha[k] = 0.f;
-                if (i < terms) {
-                    const int s = i / g.P, p = i - s * g.P;
-                    int slot = g.head + p;
-                    if (slot >= g.P) slot -= g.P;
-                    xa[k] = fdl_ny[((size_t)stream * g.Se + s) * g.P_cap + slot];
-                    ha[k] = bank_ny[(size_t)i * 2 + ear];
+                for (int k = 0; k < 8; ++k) {
+                    const int p = p0 + k * G;
+                    xa[k] = 0.f; ha[k] = 0.f;
+                    if (p < g.P) {
+                        int slot = g.head + p;
+                        if (slot >= g.P) slot -= g.P;
+                        xa[k] = xrow[slot];
+                        ha[k] = hrow[2 * p];
+                    }
                 }
-            }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) sum = fmaf(xa[k], ha[k], sum);
+                for (int k = 0; k < 8; ++k) sum = fmaf(xa[k], ha[k], sum);
+            }
         }
     }
     if constexpr (G <= 32) {

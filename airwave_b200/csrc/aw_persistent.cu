@@ -48,17 +48,19 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int PS = PaddedSize<LOG2M>::value;
     static constexpr int stage_f4 = R * (T + 2) * C;         // FDL [T][R][C] + filter [R][2 planes][C] float4
     static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
-    static constexpr int red_f4 = (MAC_SETS * R - 1) * T * 2 * C;   // partial sums of every (set, row) but the first
+    static constexpr int red_f4 = R > 1 ? (MAC_SETS * R - 1) * T * 2 * C : 0;   // partial sums of every (set, row) but the first
+                                                                                 // (R == 1: exchanged through the accumulator buffers)
     static constexpr size_t fixed_bytes = (size_t)M * sizeof(float2)                    // twiddles
                                           + (size_t)(NFT + 2 * T) * PS * sizeof(float2)  // forward buffers + accumulator buffers
                                           + (size_t)red_f4 * sizeof(float4) + (size_t)FFT_THREADS * sizeof(float) + 1024;
     static constexpr int max_stages = (int)((226 * 1024 - fixed_bytes) / stage_bytes);
-    // A ring slot must always be filled by the same producer warp and drained by the same MAC set (mbarrier parity waits are
-    // only safe for a waiter that is at most one phase behind), hence a multiple of PRODUCERS (and of MAC_SETS).
-    static constexpr int STAGES = (max_stages > 32 ? 32 : max_stages) / PRODUCERS * PRODUCERS;
+    // A ring slot is always filled by the same producer warp (slot index mod PRODUCERS) and drained by the same MAC set (slot
+    // index mod 2): mbarrier parity waits are only safe for a waiter that is at most one phase behind.  Even depth keeps
+    // the sets alternating across the wrap.
+    static constexpr int STAGES = (max_stages > 32 ? 32 : max_stages) / 2 * 2;
     static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
     static constexpr bool PREFETCH = LOG2M <= 8;             // next round's operands fetched while this round transforms
-    static_assert(STAGES >= 4 && STAGES % PRODUCERS == 0 && STAGES % MAC_SETS == 0, "ring geometry");
+    static_assert(STAGES >= 2 * PRODUCERS && STAGES % MAC_SETS == 0, "ring geometry");
 };
 
 struct PersistArgs {
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     __syncthreads();
 
     if (warp < PRODUCERS) {
-        // ===== producers: warp w issues the stages k = w, w + PRODUCERS, ... of this CTA's stage sequence =====
+        // ===== producers: warp w fills the ring slots w, w + PRODUCERS, ... every time the stage sequence comes round to them =====
         if (lane == 0) {
             const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
             const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
@@ -132,7 +134,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             };
-            for (int i = 0; i < warp; ++i) advance();
+            for (int i = 0; i < warp; ++i) advance();        // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
             int waited = -1;                                 // head_ready phases observed so far (tiles 0..waited)
             while (lt < my_tiles) {
                 const int p0 = hist ? 1 + jj * R : 0;
@@ -161,8 +163,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     bulk_g2s(dst + T * C, frow + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
                     bulk_g2s(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
                 }
-#pragma unroll
-                for (int i = 0; i < PRODUCERS; ++i) advance();
+                const int step = stage + PRODUCERS < STAGES ? PRODUCERS : STAGES - stage + warp;   // to my next slot
+                for (int i = 0; i < step; ++i) advance();
             }
         }
     } else if (warp < PRODUCERS + MAC_WARPS) {
@@ -171,70 +173,100 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         const int set = mt >> 7, w = mt & 127;
         const int r = w / C, jp = w - r * C;
         const int contributor = set * R + r;                 // partial sums are reduced in this order
-        int stage = 0, turn = 0;
+        // set q drains the ring slots of parity q, i.e. the stages k = q, q + 2, ... of the CTA's stage sequence (STAGES is even)
+        const int head0 = g.S * hs, spc = head0 + g.S;       // first head stage of / stages per column chunk
+        int stage = set;                                     // ring slot of my next stage
         unsigned phase = 0;
+        int m = set;                                         // my next stage, relative to the current chunk
+        int jj = hs > 0 ? set % hs : 0;                      // its history group (R > 1 only)
         for (int lt = 0; lt < my_tiles; ++lt) {
             for (int c = 0; c < NC; ++c) {
                 float4 aL[T], aR[T];
 #pragma unroll
                 for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
-                auto consume = [&](int nrows) {
-                    if (turn == set) {
-                        mbar_wait(&full[stage], phase);
-                        if (r < nrows) {
-                            const float4 *src = ring + stage * stage_f4;
-                            const float4 h0 = src[T * R * C + (r * 2) * C + jp], h1 = src[T * R * C + (r * 2 + 1) * C + jp];
-                            float4 x[T];
+                for (; m < spc; m += 2) {
+                    int nrows = 1;                           // head stages carry one row
+                    if (R > 1 && m < head0) nrows = min(R, g.P - 1 - jj * R);
+                    mbar_wait(&full[stage], phase);
+                    if (r < nrows) {
+                        const float4 *src = ring + stage * stage_f4;
+                        const float4 h0 = src[T * R * C + (r * 2) * C + jp], h1 = src[T * R * C + (r * 2 + 1) * C + jp];
+                        float4 x[T];
 #pragma unroll
-                            for (int u = 0; u < T; ++u) x[u] = src[(u * R + r) * C + jp];
-#pragma unroll
-                            for (int u = 0; u < T; ++u) {
-                                cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
-                                cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
-                            }
-                        }
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty[stage]);
-                    }
-                    turn ^= 1;
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
-                };
-                for (int s = 0; s < g.S; ++s)
-                    for (int jj = 0; jj < hs; ++jj) consume(min(R, g.P - 1 - jj * R));
-                for (int s = 0; s < g.S; ++s) consume(1);
-                // the FFT warps must be done with the previous tile's accumulators before they are overwritten
-                if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
-                if (contributor > 0) {
-#pragma unroll
-                    for (int u = 0; u < T; ++u) {
-                        float4 *d = red + ((size_t)((contributor - 1) * T + u) * 2) * C + jp;
-                        d[0] = aL[u];
-                        d[C] = aR[u];
-                    }
-                }
-                named_sync(BAR_RED_A, PG::MAC_THREADS);
-                if (contributor == 0) {
-#pragma unroll
-                    for (int q = 1; q < PG::MAC_SETS * R; ++q) {
+                        for (int u = 0; u < T; ++u) x[u] = src[(u * R + r) * C + jp];
 #pragma unroll
                         for (int u = 0; u < T; ++u) {
-                            const float4 *d = red + ((size_t)((q - 1) * T + u) * 2) * C + jp;
-                            const float4 l = d[0], rt = d[C];
-                            aL[u].x += l.x; aL[u].y += l.y; aL[u].z += l.z; aL[u].w += l.w;
-                            aR[u].x += rt.x; aR[u].y += rt.y; aR[u].z += rt.z; aR[u].w += rt.w;
+                            cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
+                            cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
                         }
                     }
-                    const int J = c * C + jp;   // bins 2J, 2J+1
-#pragma unroll
-                    for (int u = 0; u < T; ++u) {
-                        float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
-                        bl[pad16(2 * J)] = make_float2(aL[u].x, aL[u].y);
-                        bl[pad16(2 * J + 1)] = make_float2(aL[u].z, aL[u].w);
-                        br[pad16(2 * J)] = make_float2(aR[u].x, aR[u].y);
-                        br[pad16(2 * J + 1)] = make_float2(aR[u].z, aR[u].w);
-                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty[stage]);
+                    stage += 2;
+                    if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
+                    if (R > 1 && hs > 0) { jj += 2; while (jj >= hs) jj -= hs; }
                 }
-                named_sync(BAR_RED_B, PG::MAC_THREADS);      // the partial sums may be overwritten by the next chunk
+                m -= spc;                                    // position in the next chunk
+                if (R > 1) jj = hs > 0 ? m % hs : 0;
+                // the FFT warps must be done with the previous tile's accumulators before they are overwritten
+                if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
+                const int J = c * C + jp;                    // bins 2J, 2J+1
+                if constexpr (R == 1) {
+                    // set 1 hands its partial sums over in the accumulator buffers; set 0 adds its own and leaves the result there
+                    if (set == 1) {
+#pragma unroll
+                        for (int u = 0; u < T; ++u) {
+                            float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
+                            bl[pad16(2 * J)] = make_float2(aL[u].x, aL[u].y);
+                            bl[pad16(2 * J + 1)] = make_float2(aL[u].z, aL[u].w);
+                            br[pad16(2 * J)] = make_float2(aR[u].x, aR[u].y);
+                            br[pad16(2 * J + 1)] = make_float2(aR[u].z, aR[u].w);
+                        }
+                    }
+                    named_sync(BAR_RED_A, PG::MAC_THREADS);
+                    if (set == 0) {
+#pragma unroll
+                        for (int u = 0; u < T; ++u) {
+                            float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
+                            const float2 l0 = bl[pad16(2 * J)], l1 = bl[pad16(2 * J + 1)], r0 = br[pad16(2 * J)], r1 = br[pad16(2 * J + 1)];
+                            bl[pad16(2 * J)] = make_float2(aL[u].x + l0.x, aL[u].y + l0.y);
+                            bl[pad16(2 * J + 1)] = make_float2(aL[u].z + l1.x, aL[u].w + l1.y);
+                            br[pad16(2 * J)] = make_float2(aR[u].x + r0.x, aR[u].y + r0.y);
+                            br[pad16(2 * J + 1)] = make_float2(aR[u].z + r1.x, aR[u].w + r1.y);
+                        }
+                    }
+                } else {
+                    if (contributor > 0) {
+#pragma unroll
+                        for (int u = 0; u < T; ++u) {
+                            float4 *d = red + ((size_t)((contributor - 1) * T + u) * 2) * C + jp;
+                            d[0] = aL[u];
+                            d[C] = aR[u];
+                        }
+                    }
+                    named_sync(BAR_RED_A, PG::MAC_THREADS);
+                    if (contributor == 0) {
+#pragma unroll
+                        for (int q = 1; q < PG::MAC_SETS * R; ++q) {
+#pragma unroll
+                            for (int u = 0; u < T; ++u) {
+                                const float4 *d = red + ((size_t)((q - 1) * T + u) * 2) * C + jp;
+                                const float4 l = d[0], rt = d[C];
+                                aL[u].x += l.x; aL[u].y += l.y; aL[u].z += l.z; aL[u].w += l.w;
+                                aR[u].x += rt.x; aR[u].y += rt.y; aR[u].z += rt.z; aR[u].w += rt.w;
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < T; ++u) {
+                            float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
+                            bl[pad16(2 * J)] = make_float2(aL[u].x, aL[u].y);
+                            bl[pad16(2 * J + 1)] = make_float2(aL[u].z, aL[u].w);
+                            br[pad16(2 * J)] = make_float2(aR[u].x, aR[u].y);
+                            br[pad16(2 * J + 1)] = make_float2(aR[u].z, aR[u].w);
+                        }
+                    }
+                    named_sync(BAR_RED_B, PG::MAC_THREADS);  // the partial sums may be overwritten by the next chunk
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_ready);
