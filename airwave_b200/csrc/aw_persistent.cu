@@ -35,18 +35,29 @@ namespace aw {
 template <int LOG2M, int T> struct PGeo {
     static_assert(T == 2 || T == 4, "tile of 2 or 4 streams");
     static constexpr int M = 1 << LOG2M, halfB = M / 2;
-    static constexpr int C = halfB < 128 ? halfB : 128;      // bin pairs per column chunk
+    // Stage shape.  A bulk copy costs its issuing thread ~155 cycles and the copy engine ~40 cycles whatever its size
+    // (tools/tmabw.cu), so a stage is built from few, large copies: RS consecutive partitions of one speaker x C bin pairs.
+    //   B <= 256 : whole rows (C = B/2), RS = 2 * 128/C rows  -> 4 KB of FDL per stream and copy, 8 KB of filter in one copy
+    //   B  = 512 : whole rows (C = 256), one row              -> the same sizes; a MAC thread owns CW = 2 bin pairs
+    //   B >= 1024: column chunks of 128 bin pairs, one row    -> 2 KB copies (shared memory leaves no room for more)
+    static constexpr int C = halfB < 128 ? halfB : (LOG2M == 9 ? 256 : 128);   // bin pairs per column chunk
     static constexpr int NC = halfB / C;                     // column chunks per row
-    static constexpr int R = 128 / C;                        // (speaker, partition) pairs per stage
-    static constexpr int MAC_SETS = 2;                       // sets of 128 MAC threads; set q consumes the stages k = q (mod 2)
+    static constexpr int CW = C > 128 ? C / 128 : 1;         // bin pairs per MAC thread
+    static constexpr int R = C < 128 ? 128 / C : 1;          // rows side by side in a MAC set (one per C threads)
+    static constexpr int RT = LOG2M <= 8 ? 2 : 1;            // rows per MAC thread
+    static constexpr int RS = R * RT;                        // rows ((speaker, partition) pairs, consecutive partitions) per stage
+    static constexpr int MAC_SETS = 2;                       // sets of 128 MAC threads; set q drains the ring slots of parity q
     static constexpr int MAC_THREADS = MAC_SETS * 128;
     static constexpr int G = RegFft<LOG2M>::G;               // threads per transform
     static constexpr int FFT_THREADS = 8 * G <= 128 ? 128 : 256;
     static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
     static constexpr int PRODUCERS = 4;                      // producer warps, one issuing lane each
     static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
+    // 640-thread variants are launched with 96 registers per thread; the producer warpgroup gives most of its share back and
+    // the MAC warpgroups take it (setmaxnreg), so that 2 bin pairs x T streams x 2 ears of accumulators stay in registers.
+    static constexpr bool REBALANCE = THREADS > 512 && CW > 1;
     static constexpr int PS = PaddedSize<LOG2M>::value;
-    static constexpr int stage_f4 = R * (T + 2) * C;         // FDL [T][R][C] + filter [R][2 planes][C] float4
+    static constexpr int stage_f4 = RS * (T + 2) * C;        // FDL [T][RS][C] + filter [RS][2 planes][C] float4
     static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
     static constexpr int red_f4 = R > 1 ? (MAC_SETS * R - 1) * T * 2 * C : 0;   // partial sums of every (set, row) but the first
                                                                                  // (R == 1: exchanged through the accumulator buffers)
@@ -60,7 +71,8 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int STAGES = (max_stages > 32 ? 32 : max_stages) / 2 * 2;
     static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
     static constexpr bool PREFETCH = LOG2M <= 8;             // next round's operands fetched while this round transforms
-    static_assert(STAGES >= 2 * PRODUCERS && STAGES % MAC_SETS == 0, "ring geometry");
+    static_assert(STAGES >= PRODUCERS && STAGES % MAC_SETS == 0, "ring geometry");
+    static_assert(NC == 1 || RS == 1, "column chunks carry one row per stage");
 };
 
 struct PersistArgs {
@@ -80,7 +92,7 @@ template <int LOG2M, int T>
 __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const PersistArgs a)
 {
     using PG = PGeo<LOG2M, T>;
-    constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, G = PG::G, NFT = PG::NFT;
+    constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, RT = PG::RT, RS = PG::RS, CW = PG::CW, G = PG::G, NFT = PG::NFT;
     constexpr int STAGES = PG::STAGES, PS = PG::PS, stage_f4 = PG::stage_f4, PRODUCERS = PG::PRODUCERS;
     constexpr int MAC_WARPS = PG::MAC_THREADS / 32, SET_WARPS = 4, FFT_WARPS = PG::FFT_THREADS / 32;
     constexpr int BAR_RED_A = 1, BAR_RED_B = 2, BAR_FFT0 = 4;
@@ -102,7 +114,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     const int n_tiles = (g.n_streams + T - 1) / T;
     const int last = g.first_stream + g.n_streams - 1;
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int hs = (g.P - 1 + R - 1) / R;                // history stages per speaker (groups of R partitions)
+    const int hs = (g.P - 1 + RS - 1) / RS;              // history stages per speaker (groups of RS partitions)
 
     for (int k = tid; k < M; k += PG::THREADS) tw[k] = a.tw[k];
     if (tid == 0) {
@@ -116,6 +128,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     __syncthreads();
 
     if (warp < PRODUCERS) {
+        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         // ===== producers: warp w fills the ring slots w, w + PRODUCERS, ... every time the stage sequence comes round to them =====
         if (lane == 0) {
             const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
@@ -137,8 +150,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             for (int i = 0; i < warp; ++i) advance();        // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
             int waited = -1;                                 // head_ready phases observed so far (tiles 0..waited)
             while (lt < my_tiles) {
-                const int p0 = hist ? 1 + jj * R : 0;
-                const int nrows = hist ? min(R, g.P - p0) : 1;
+                const int p0 = hist ? 1 + jj * RS : 0;
+                const int nrows = hist ? min(RS, g.P - p0) : 1;
                 // head rows of tile lt exist once the FFT warps have published them; phases are observed strictly in order
                 const int need = (c > 0 || !hist) ? lt : lt - 1;
                 while (waited < need) { ++waited; mbar_wait(&head_ready[waited & 1], (unsigned)((waited >> 1) & 1)); }
@@ -152,13 +165,13 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
 #pragma unroll
                 for (int u = 0; u < T; ++u) {
                     const float4 *row = fdl4 + (size_t)min(s0 + u, last) * stream_stride + (size_t)s * g.P_cap * halfB + c * C;
-                    bulk_g2s(dst + (u * R) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage]);
-                    if (R > 1 && n1 < nrows)
-                        bulk_g2s(dst + (u * R + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage]);
+                    bulk_g2s(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage]);
+                    if (RS > 1 && n1 < nrows)
+                        bulk_g2s(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage]);
                 }
                 const float4 *frow = a.bank + ((size_t)s * g.P + p0) * M;
-                if (NC == 1) {                               // whole rows: both planes of R consecutive partitions are contiguous
-                    bulk_g2s(dst + T * R * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage]);
+                if (NC == 1) {                               // whole rows: both planes of RS consecutive partitions are contiguous
+                    bulk_g2s(dst + T * RS * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage]);
                 } else {
                     bulk_g2s(dst + T * C, frow + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
                     bulk_g2s(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
@@ -168,80 +181,100 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             }
         }
     } else if (warp < PRODUCERS + MAC_WARPS) {
+        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         // ===== MAC warps: set q consumes the stages k = q (mod 2); a thread owns one bin pair of one row, all T streams =====
         const int mt = tid - 32 * PRODUCERS;
         const int set = mt >> 7, w = mt & 127;
-        const int r = w / C, jp = w - r * C;
+        const int r = C < 128 ? w / C : 0, jp = C < 128 ? w - r * C : w;
         const int contributor = set * R + r;                 // partial sums are reduced in this order
         // set q drains the ring slots of parity q, i.e. the stages k = q, q + 2, ... of the CTA's stage sequence (STAGES is even)
         const int head0 = g.S * hs, spc = head0 + g.S;       // first head stage of / stages per column chunk
         int stage = set;                                     // ring slot of my next stage
         unsigned phase = 0;
         int m = set;                                         // my next stage, relative to the current chunk
-        int jj = hs > 0 ? set % hs : 0;                      // its history group (R > 1 only)
+        int jj = hs > 0 ? set % hs : 0;                      // its history group (RS > 1 only)
         for (int lt = 0; lt < my_tiles; ++lt) {
             for (int c = 0; c < NC; ++c) {
-                float4 aL[T], aR[T];
+                float4 aL[CW][T], aR[CW][T];
 #pragma unroll
-                for (int u = 0; u < T; ++u) { aL[u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[u] = aL[u]; }
+                for (int v = 0; v < CW; ++v)
+#pragma unroll
+                    for (int u = 0; u < T; ++u) { aL[v][u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[v][u] = aL[v][u]; }
                 for (; m < spc; m += 2) {
                     int nrows = 1;                           // head stages carry one row
-                    if (R > 1 && m < head0) nrows = min(R, g.P - 1 - jj * R);
+                    if (RS > 1 && m < head0) nrows = min(RS, g.P - 1 - jj * RS);
                     mbar_wait(&full[stage], phase);
-                    if (r < nrows) {
-                        const float4 *src = ring + stage * stage_f4;
-                        const float4 h0 = src[T * R * C + (r * 2) * C + jp], h1 = src[T * R * C + (r * 2 + 1) * C + jp];
-                        float4 x[T];
+                    const float4 *src = ring + stage * stage_f4;
 #pragma unroll
-                        for (int u = 0; u < T; ++u) x[u] = src[(u * R + r) * C + jp];
+                    for (int i = 0; i < RT; ++i) {
+                        const int row = r + R * i;
+                        if (row < nrows) {
 #pragma unroll
-                        for (int u = 0; u < T; ++u) {
-                            cmac2f(aL[u], x[u], h0.x, h0.y, h1.x, h1.y);
-                            cmac2f(aR[u], x[u], h0.z, h0.w, h1.z, h1.w);
+                            for (int v = 0; v < CW; ++v) {
+                                const int col = jp + 128 * v;
+                                const float4 h0 = src[T * RS * C + (row * 2) * C + col], h1 = src[T * RS * C + (row * 2 + 1) * C + col];
+                                float4 x[T];
+#pragma unroll
+                                for (int u = 0; u < T; ++u) x[u] = src[(u * RS + row) * C + col];
+#pragma unroll
+                                for (int u = 0; u < T; ++u) {
+                                    cmac2f(aL[v][u], x[u], h0.x, h0.y, h1.x, h1.y);
+                                    cmac2f(aR[v][u], x[u], h0.z, h0.w, h1.z, h1.w);
+                                }
+                            }
                         }
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[stage]);
                     stage += 2;
                     if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
-                    if (R > 1 && hs > 0) { jj += 2; while (jj >= hs) jj -= hs; }
+                    if (RS > 1 && hs > 0) { jj += 2; while (jj >= hs) jj -= hs; }
                 }
                 m -= spc;                                    // position in the next chunk
-                if (R > 1) jj = hs > 0 ? m % hs : 0;
+                if (RS > 1) jj = hs > 0 ? m % hs : 0;
                 // the FFT warps must be done with the previous tile's accumulators before they are overwritten
                 if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
-                const int J = c * C + jp;                    // bins 2J, 2J+1
                 if constexpr (R == 1) {
                     // set 1 hands its partial sums over in the accumulator buffers; set 0 adds its own and leaves the result there
                     if (set == 1) {
 #pragma unroll
-                        for (int u = 0; u < T; ++u) {
-                            float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
-                            bl[pad16(2 * J)] = make_float2(aL[u].x, aL[u].y);
-                            bl[pad16(2 * J + 1)] = make_float2(aL[u].z, aL[u].w);
-                            br[pad16(2 * J)] = make_float2(aR[u].x, aR[u].y);
-                            br[pad16(2 * J + 1)] = make_float2(aR[u].z, aR[u].w);
+                        for (int v = 0; v < CW; ++v) {
+                            const int J = c * C + jp + 128 * v;      // bins 2J, 2J+1
+#pragma unroll
+                            for (int u = 0; u < T; ++u) {
+                                float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
+                                bl[pad16(2 * J)] = make_float2(aL[v][u].x, aL[v][u].y);
+                                bl[pad16(2 * J + 1)] = make_float2(aL[v][u].z, aL[v][u].w);
+                                br[pad16(2 * J)] = make_float2(aR[v][u].x, aR[v][u].y);
+                                br[pad16(2 * J + 1)] = make_float2(aR[v][u].z, aR[v][u].w);
+                            }
                         }
                     }
                     named_sync(BAR_RED_A, PG::MAC_THREADS);
                     if (set == 0) {
 #pragma unroll
-                        for (int u = 0; u < T; ++u) {
-                            float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
-                            const float2 l0 = bl[pad16(2 * J)], l1 = bl[pad16(2 * J + 1)], r0 = br[pad16(2 * J)], r1 = br[pad16(2 * J + 1)];
-                            bl[pad16(2 * J)] = make_float2(aL[u].x + l0.x, aL[u].y + l0.y);
-                            bl[pad16(2 * J + 1)] = make_float2(aL[u].z + l1.x, aL[u].w + l1.y);
-                            br[pad16(2 * J)] = make_float2(aR[u].x + r0.x, aR[u].y + r0.y);
-                            br[pad16(2 * J + 1)] = make_float2(aR[u].z + r1.x, aR[u].w + r1.y);
+                        for (int v = 0; v < CW; ++v) {
+                            const int J = c * C + jp + 128 * v;
+#pragma unroll
+                            for (int u = 0; u < T; ++u) {
+                                float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
+                                const float2 l0 = bl[pad16(2 * J)], l1 = bl[pad16(2 * J + 1)], r0 = br[pad16(2 * J)], r1 = br[pad16(2 * J + 1)];
+                                bl[pad16(2 * J)] = make_float2(aL[v][u].x + l0.x, aL[v][u].y + l0.y);
+                                bl[pad16(2 * J + 1)] = make_float2(aL[v][u].z + l1.x, aL[v][u].w + l1.y);
+                                br[pad16(2 * J)] = make_float2(aR[v][u].x + r0.x, aR[v][u].y + r0.y);
+                                br[pad16(2 * J + 1)] = make_float2(aR[v][u].z + r1.x, aR[v][u].w + r1.y);
+                            }
                         }
                     }
                 } else {
+                    static_assert(R == 1 || CW == 1, "narrow rows: one bin pair per thread");
+                    const int J = c * C + jp;                // bins 2J, 2J+1
                     if (contributor > 0) {
 #pragma unroll
                         for (int u = 0; u < T; ++u) {
                             float4 *d = red + ((size_t)((contributor - 1) * T + u) * 2) * C + jp;
-                            d[0] = aL[u];
-                            d[C] = aR[u];
+                            d[0] = aL[0][u];
+                            d[C] = aR[0][u];
                         }
                     }
                     named_sync(BAR_RED_A, PG::MAC_THREADS);
@@ -252,17 +285,17 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                             for (int u = 0; u < T; ++u) {
                                 const float4 *d = red + ((size_t)((q - 1) * T + u) * 2) * C + jp;
                                 const float4 l = d[0], rt = d[C];
-                                aL[u].x += l.x; aL[u].y += l.y; aL[u].z += l.z; aL[u].w += l.w;
-                                aR[u].x += rt.x; aR[u].y += rt.y; aR[u].z += rt.z; aR[u].w += rt.w;
+                                aL[0][u].x += l.x; aL[0][u].y += l.y; aL[0][u].z += l.z; aL[0][u].w += l.w;
+                                aR[0][u].x += rt.x; aR[0][u].y += rt.y; aR[0][u].z += rt.z; aR[0][u].w += rt.w;
                             }
                         }
 #pragma unroll
                         for (int u = 0; u < T; ++u) {
                             float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
-                            bl[pad16(2 * J)] = make_float2(aL[u].x, aL[u].y);
-                            bl[pad16(2 * J + 1)] = make_float2(aL[u].z, aL[u].w);
-                            br[pad16(2 * J)] = make_float2(aR[u].x, aR[u].y);
-                            br[pad16(2 * J + 1)] = make_float2(aR[u].z, aR[u].w);
+                            bl[pad16(2 * J)] = make_float2(aL[0][u].x, aL[0][u].y);
+                            bl[pad16(2 * J + 1)] = make_float2(aL[0][u].z, aL[0][u].w);
+                            br[pad16(2 * J)] = make_float2(aR[0][u].x, aR[0][u].y);
+                            br[pad16(2 * J + 1)] = make_float2(aR[0][u].z, aR[0][u].w);
                         }
                     }
                     named_sync(BAR_RED_B, PG::MAC_THREADS);  // the partial sums may be overwritten by the next chunk
@@ -273,6 +306,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         }
     } else {
         // ===== FFT warps =====
+        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         using F = RegFft<LOG2M>;
         const int ft = tid - 32 * PRODUCERS - PG::MAC_THREADS;
         const int f = ft / G, t = ft - f * G;
