@@ -24,7 +24,7 @@
 //                       (accumulators handed over through shared memory, acc_ready/acc_free mbarriers).
 //
 // The head partition (p = 0) is streamed like any other row: the FFT warps publish it with a generic->async proxy fence
-// + the head_ready mbarrier, which the producer waits on before it issues the first head row of a tile.
+// + a monotonic shared-memory count (release/acquire), which a producer checks before it issues a head row of a tile.
 // Stage order inside a tile (and column chunk): for every speaker its history partitions p = 1..P-1 in groups of R, then
 // the S head rows — the same for every tile size and stream count, so a stream's output does not depend on how many
 // streams the engine renders or on which GPU it lives.
@@ -51,11 +51,19 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int G = RegFft<LOG2M>::G;               // threads per transform
     static constexpr int FFT_THREADS = 8 * G <= 128 ? 128 : 256;
     static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
-    static constexpr int PRODUCERS = 4;                      // producer warps, one issuing lane each
+    // producer warps, one issuing lane each.  B = 512: three, so that the 19 warps get 104 registers each (the MAC threads hold
+    // 2 bin pairs x T streams x 2 ears of accumulators) and the 6 ring slots divide evenly among them.
+    static constexpr int PRODUCERS = LOG2M == 9 ? 3 : 4;
     static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
-    // 640-thread variants are launched with 96 registers per thread; the producer warpgroup gives most of its share back and
-    // the MAC warpgroups take it (setmaxnreg), so that 2 bin pairs x T streams x 2 ears of accumulators stay in registers.
-    static constexpr bool REBALANCE = THREADS > 512 && CW > 1;
+    // Experiment switch (off): hand registers from the producer warpgroup to the MAC warpgroups with setmaxnreg.  It produced
+    // sporadic whole-tile corruption at B = 512, T = 4 that the register indices in the SASS do not explain; see DESIGN.md.
+#ifndef AW_KP_REBALANCE
+#define AW_KP_REBALANCE 0
+#endif
+#ifndef AW_KP_PRODUCER_REGS
+#define AW_KP_PRODUCER_REGS 40
+#endif
+    static constexpr bool REBALANCE = AW_KP_REBALANCE && PRODUCERS == 4 && THREADS > 512 && CW > 1;
     static constexpr int PS = PaddedSize<LOG2M>::value;
     static constexpr int stage_f4 = RS * (T + 2) * C;        // FDL [T][RS][C] + filter [RS][2 planes][C] float4
     static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
@@ -105,9 +113,9 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     float *part = reinterpret_cast<float *>(red + PG::red_f4);
     uint64_t *full = reinterpret_cast<uint64_t *>(part + PG::FFT_THREADS);
     uint64_t *empty = full + STAGES;
-    uint64_t *head_ready = empty + STAGES;   // [2], alternating by local tile parity
-    uint64_t *acc_ready = head_ready + 2;
+    uint64_t *acc_ready = empty + STAGES;
     uint64_t *acc_free = acc_ready + 1;
+    unsigned *heads_done = reinterpret_cast<unsigned *>(acc_free + 1);   // FFT warps that have published their head rows, all tiles so far
 
     const BlockGeom &g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -119,8 +127,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     for (int k = tid; k < M; k += PG::THREADS) tw[k] = a.tw[k];
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], SET_WARPS); }
-        mbar_init(&head_ready[0], FFT_WARPS);
-        mbar_init(&head_ready[1], FFT_WARPS);
+        *heads_done = 0;
         mbar_init(acc_ready, MAC_WARPS);
         mbar_init(acc_free, FFT_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -128,7 +135,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     __syncthreads();
 
     if (warp < PRODUCERS) {
-        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AW_KP_PRODUCER_REGS));
         // ===== producers: warp w fills the ring slots w, w + PRODUCERS, ... every time the stage sequence comes round to them =====
         if (lane == 0) {
             const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
@@ -148,13 +155,17 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             };
             for (int i = 0; i < warp; ++i) advance();        // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
-            int waited = -1;                                 // head_ready phases observed so far (tiles 0..waited)
             while (lt < my_tiles) {
                 const int p0 = hist ? 1 + jj * RS : 0;
                 const int nrows = hist ? min(RS, g.P - p0) : 1;
-                // head rows of tile lt exist once the FFT warps have published them; phases are observed strictly in order
-                const int need = (c > 0 || !hist) ? lt : lt - 1;
-                while (waited < need) { ++waited; mbar_wait(&head_ready[waited & 1], (unsigned)((waited >> 1) & 1)); }
+                // head rows of tile lt exist once every FFT warp has published them (a monotonic count: no phase to alias)
+                if (!hist) {
+                    const unsigned need = (unsigned)(FFT_WARPS * (lt + 1));
+                    unsigned seen;
+                    do {
+                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(heads_done)) : "memory");
+                    } while (seen < need);
+                }
                 const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
                 int slot = g.head + p0;
                 if (slot >= g.P) slot -= g.P;                // modulus is partitionCount (Q4)
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(&head_ready[lt & 1]);
+            if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(heads_done)) : "memory");
         };
 
         auto inverse_tile = [&](int lt) {
