@@ -171,7 +171,13 @@ cudaError_t launch_synth_fill(float *out, int first_stream, int n_streams, int S
 // ------------------------------------------------------------------------------------------------
 // K5  eq: one thread per (stream, ear) channel; filter state in registers (FMAX bucket), float64.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double flush_subnormal(double v) { return fabs(v) < 1e-30 ? 0.0 : v; }   // :94-97
+// abs(v) < 1e-30 ? 0 : v (:94-97), with the comparison done on the bit pattern (|v| as an unsigned integer orders like |v| for
+// non-NaN doubles, and NaN compares "not below" either way) so that it stays off the float64 pipe, the scarce resource of K5.
+__device__ __forceinline__ double flush_subnormal(double v)
+{
+    const unsigned long long mag = (unsigned long long)__double_as_longlong(v) & 0x7fffffffffffffffULL;
+    return mag < 0x39B4484BFEEBC2A0ULL ? 0.0 : v;       // 0x39B4484BFEEBC2A0 = 1e-30
+}
 
 template <int FMAX>
 __device__ __forceinline__ double biquad_cascade(double x, const EqProgram *__restrict__ prog, int nf, double (&z1)[FMAX], double (&z2)[FMAX])
@@ -242,6 +248,68 @@ __global__ void __launch_bounds__(64) k_eq(const EqLaunch l, double *__restrict_
     }
 }
 
+// Steady state (no crossfade), 1..32 filters: the cascade as a systolic array across the lanes of a warp.  Lane f of a group of
+// `gw` = n_filters lanes owns biquad f of one (stream, ear) channel — coefficients and both state words in registers — and at
+// step t filters sample t - f, taking its input from lane f-1's output of the previous step (two 32-bit shuffles).  The
+// per-sample critical path is one biquad instead of n_filters, every lane does useful float64 work, and a warp carries
+// floor(32/gw) channels.  Same operations in the same order per biquad as ParametricEqualizerState.process (:65-90): bit-exact.
+__global__ void __launch_bounds__(128) k_eq_systolic(const EqLaunch l, int gw, double *__restrict__ zstate, StridedOut io)
+{
+    __shared__ float stage_s[4][1024];                      // per warp: `groups` channels x `chunk` frames, staged coalesced
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int groups = 32 / gw;
+    const int g = lane / gw, f = lane - g * gw;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long ch0 = warp * groups;                    // first channel (= stream*2 + ear within the launch) of this warp
+    const long long total = (long long)l.n_streams * 2;
+    if (ch0 >= total) return;                               // whole warp idle
+    const long long ch = ch0 + g;
+    const bool live = g < groups && ch < total;
+    const int stream = l.first_stream + (int)(live ? ch >> 1 : 0), ear = (int)(ch & 1);
+    const EqProgram *prog = l.from;
+    const double pre = prog->preamp_linear;
+    double b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, z1 = 0, z2 = 0;
+    double *zp = zstate + ((((size_t)stream * 2 + l.from_voice) * 2 + ear) * 64 + (live ? f : 0)) * 2;
+    if (live) {
+        b0 = prog->coef[f][0]; b1 = prog->coef[f][1]; b2 = prog->coef[f][2]; a1 = prog->coef[f][3]; a2 = prog->coef[f][4];
+        z1 = zp[0]; z2 = zp[1];
+    }
+    const int chunk = (1024 / groups) & ~31;                // frames per channel staged at a time (a multiple of 32)
+    float *mine = stage_s[wid] + (g < groups ? g : 0) * chunk;
+    for (int c0 = 0; c0 < l.seg_len; c0 += chunk) {
+        const int cl = min(chunk, l.seg_len - c0);
+        for (int q = 0; q < groups && ch0 + q < total; ++q) {   // coalesced: the warp copies one channel's frames at a time
+            const long long cq = ch0 + q;
+            const float *src = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + l.seg_start + c0;
+            for (int i = lane; i < cl; i += 32) stage_s[wid][q * chunk + i] = src[i];
+        }
+        __syncwarp();
+        double y = 0.0;                                     // my output of the previous step
+        for (int t = 0; t < cl + gw - 1; ++t) {
+            const double up = __shfl_up_sync(0xffffffffu, y, 1);
+            const int i = t - f;                            // the sample this lane filters now
+            if (live && i >= 0 && i < cl) {
+                const double x = f == 0 ? __dmul_rn((double)mine[i], pre) : up;   // preamp first (:66)
+                // no FMA contraction: the reference (and the oracle) round every product and sum (:73-75)
+                y = __dadd_rn(__dmul_rn(b0, x), z1);
+                const double n1 = __dadd_rn(__dsub_rn(__dmul_rn(b1, x), __dmul_rn(a1, y)), z2);
+                const double n2 = __dsub_rn(__dmul_rn(b2, x), __dmul_rn(a2, y));
+                z1 = flush_subnormal(n1);
+                z2 = flush_subnormal(n2);
+                if (f == gw - 1) mine[i] = (float)y;        // :88-89 (in place: sample i was consumed gw-1 steps ago)
+            }
+        }
+        __syncwarp();
+        for (int q = 0; q < groups && ch0 + q < total; ++q) {
+            const long long cq = ch0 + q;
+            float *dst = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + l.seg_start + c0;
+            for (int i = lane; i < cl; i += 32) dst[i] = stage_s[wid][q * chunk + i];
+        }
+        __syncwarp();
+    }
+    if (live) { zp[0] = z1; zp[1] = z2; }
+}
+
 template <int FMAX>
 static cudaError_t launch_eq_t(const EqLaunch &l, double *z, StridedOut io, cudaStream_t st)
 {
@@ -254,6 +322,12 @@ static cudaError_t launch_eq_t(const EqLaunch &l, double *z, StridedOut io, cuda
 cudaError_t launch_eq(const EqLaunch &l, int max_filters, double *z, StridedOut io, cudaStream_t st)
 {
     if (l.n_streams <= 0 || l.seg_len <= 0) return cudaSuccess;
+    if (l.to == nullptr && max_filters >= 1 && max_filters <= 32) {   // max_filters = the active state's filter count here
+        const int groups = 32 / max_filters;
+        const long long warps = ((long long)l.n_streams * 2 + groups - 1) / groups;
+        k_eq_systolic<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(l, max_filters, z, io);
+        return cudaGetLastError();
+    }
     if (max_filters <= 4) return launch_eq_t<4>(l, z, io, st);
     if (max_filters <= 8) return launch_eq_t<8>(l, z, io, st);
     if (max_filters <= 16) return launch_eq_t<16>(l, z, io, st);

@@ -39,8 +39,8 @@ template <int LOG2M, int T> struct PGeo {
     // (tools/tmabw.cu), so a stage is built from few, large copies: RS consecutive partitions of one speaker x C bin pairs.
     //   B <= 256 : whole rows (C = B/2), RS = 2 * 128/C rows  -> 4 KB of FDL per stream and copy, 8 KB of filter in one copy
     //   B  = 512 : whole rows (C = 256), one row              -> the same sizes; a MAC thread owns CW = 2 bin pairs
-    //   B >= 1024: column chunks of 128 bin pairs, one row    -> 2 KB copies (shared memory leaves no room for more)
-    static constexpr int C = halfB < 128 ? halfB : (LOG2M == 9 ? 256 : 128);   // bin pairs per column chunk
+    //   B >= 1024: column chunks of 256 bin pairs, one row    -> 4 KB copies for the FDL and for each filter plane
+    static constexpr int C = halfB < 128 ? halfB : (LOG2M >= 9 ? 256 : 128);   // bin pairs per column chunk
     static constexpr int NC = halfB / C;                     // column chunks per row
     static constexpr int CW = C > 128 ? C / 128 : 1;         // bin pairs per MAC thread
     static constexpr int R = C < 128 ? 128 / C : 1;          // rows side by side in a MAC set (one per C threads)
@@ -51,9 +51,9 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int G = RegFft<LOG2M>::G;               // threads per transform
     static constexpr int FFT_THREADS = 8 * G <= 128 ? 128 : 256;
     static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
-    // producer warps, one issuing lane each.  B = 512: three, so that the 19 warps get 104 registers each (the MAC threads hold
-    // 2 bin pairs x T streams x 2 ears of accumulators) and the 6 ring slots divide evenly among them.
-    static constexpr int PRODUCERS = LOG2M == 9 ? 3 : 4;
+    // producer warps, one issuing lane each.  B >= 512 with T = 4: three, so that the 19 warps get 104 registers each (the MAC
+    // threads hold 2 bin pairs x 4 streams x 2 ears of accumulators); at B = 512 the 6 ring slots divide evenly among them.
+    static constexpr int PRODUCERS = LOG2M >= 9 && T == 4 ? 3 : 4;
     static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
     // Experiment switch (off): hand registers from the producer warpgroup to the MAC warpgroups with setmaxnreg.  It produced
     // sporadic whole-tile corruption at B = 512, T = 4 that the register indices in the SASS do not explain; see DESIGN.md.

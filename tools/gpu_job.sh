@@ -1,5 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python tools/dbg_twins2.py 2>&1 | grep -v "^   stream" | tail -10
-PYTEST_TIMEOUT=1800 PYTEST_ARGS="--timeout 900" bash tools/gpu_check.sh
-bash tools/bench_all.sh C2 C3 C5-512
+BENCH_ENV="AW_PERSISTENT_DEBUG=3" bash tools/bench_all.sh C5-1024 C5-2048 C2 C5-64
+BENCH_ENV="AW_PERSISTENT_DEBUG=1" bash tools/bench_all.sh C5-1024 C5-2048
+BENCH_ENV="AW_PERSISTENT_DEBUG=2" bash tools/bench_all.sh C5-1024 C5-2048
