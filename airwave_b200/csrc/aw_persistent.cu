@@ -140,6 +140,9 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         if (lane == 0) {
             const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
             const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
+            // L2 priorities: history rows are read once per launch (evict first) — they must not push out the head rows the FFT
+            // warps have just written, nor the filter bank every tile re-reads (evict last)
+            const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
             // position of this producer in the stage sequence, advanced one stage at a time (no divisions on the issue path):
             // tile lt, column chunk c, and inside the chunk either history group jj of speaker s or the head row of speaker s
             int lt = 0, c = 0, s = 0, jj = 0, stage = 0;
@@ -176,16 +179,17 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
 #pragma unroll
                 for (int u = 0; u < T; ++u) {
                     const float4 *row = fdl4 + (size_t)min(s0 + u, last) * stream_stride + (size_t)s * g.P_cap * halfB + c * C;
-                    bulk_g2s(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage]);
+                    const uint64_t pol = hist ? pol_stream : pol_keep;
+                    bulk_g2s_hint(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage], pol);
                     if (RS > 1 && n1 < nrows)
-                        bulk_g2s(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage]);
+                        bulk_g2s_hint(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage], pol);
                 }
                 const float4 *frow = a.bank + ((size_t)s * g.P + p0) * M;
                 if (NC == 1) {                               // whole rows: both planes of RS consecutive partitions are contiguous
-                    bulk_g2s(dst + T * RS * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage]);
+                    bulk_g2s_hint(dst + T * RS * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage], pol_keep);
                 } else {
-                    bulk_g2s(dst + T * C, frow + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
-                    bulk_g2s(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage]);
+                    bulk_g2s_hint(dst + T * C, frow + c * C, (unsigned)(C * sizeof(float4)), &full[stage], pol_keep);
+                    bulk_g2s_hint(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage], pol_keep);
                 }
                 const int step = stage + PRODUCERS < STAGES ? PRODUCERS : STAGES - stage + warp;   // to my next slot
                 for (int i = 0; i < step; ++i) advance();

@@ -1,5 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-BENCH_ENV="AW_PERSISTENT_DEBUG=3" bash tools/bench_all.sh C5-1024 C5-2048 C2 C5-64
-BENCH_ENV="AW_PERSISTENT_DEBUG=1" bash tools/bench_all.sh C5-1024 C5-2048
-BENCH_ENV="AW_PERSISTENT_DEBUG=2" bash tools/bench_all.sh C5-1024 C5-2048
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "paths_agree or c2_full" --timeout 600 > gpurun_out/pytest_paths.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_paths.log
+bash tools/bench_all.sh C2 C3 C4 C5-512
