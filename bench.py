@@ -178,7 +178,7 @@ def cpu_sample(S, B, pcm, rate, l_idx, r_idx, budget_s, threads=0):
     batch = oracle.CpuBatch(streams, S, B, h)
     sec, _ = batch.step(2, cores)                          # pilot (also warms the FDL)
     per_block = max(sec / 2, 1e-6)
-    blocks = int(max(4, min(4000, budget_s / per_block)))
+    blocks = int(max(4, min(200000, budget_s / per_block)))     # ~budget_s seconds of CPU work
     sec, _ = batch.step(blocks, cores)
     value = streams * blocks * (B / FS) / sec
     return value, cores, f"{streams} streams x {blocks} blocks of {B} frames, one stream per thread, {cores} threads, {sec:.2f} s"
@@ -199,15 +199,18 @@ def run_reference(args):
     cores = oracle.max_threads()
     streams = max(cores * 4, 8)
     batch = oracle.CpuBatch(streams, S, B, h)
-    # size the per-step sample so K steps end within a few minutes even for long BRIRs
-    blocks_per_step = 8      # amortises the per-step thread start-up over ~10 ms of work
-    pilot, _ = batch.step(blocks_per_step, cores)
-    total_est = pilot * (args.steps + args.warmup)
-    while total_est > 150 and streams > cores:
+    # size the per-step sample: long enough (~0.25 s) that thread start-up does not count against the CPU, short enough
+    # that the whole --steps/--warmup run ends within a few minutes even for long BRIRs
+    pilot, _ = batch.step(8, cores)
+    pilot, _ = batch.step(8, cores)
+    per_block = max(pilot / 8, 1e-6)
+    step_budget = min(0.25, 150.0 / max(args.steps + args.warmup, 1))
+    blocks_per_step = int(max(1, min(4000, step_budget / per_block)))
+    while per_block * blocks_per_step * (args.steps + args.warmup) > 150 and streams > cores:
         streams //= 2
         batch = oracle.CpuBatch(streams, S, B, h)
-        pilot, _ = batch.step(blocks_per_step, cores)
-        total_est = pilot * (args.steps + args.warmup)
+        pilot, _ = batch.step(8, cores)
+        per_block = max(pilot / 8, 1e-6)
     for _ in range(args.warmup):
         batch.step(blocks_per_step, cores)
     t = 0.0
@@ -423,7 +426,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
