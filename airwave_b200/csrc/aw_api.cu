@@ -134,6 +134,10 @@ struct aw_engine {
     int persistentTile = 0;        // streams per tile of KP (4 or 2)
     int persistentCtas = 0;        // CTAs of KP (default: one per SM)
     int persistentDebug = 0;       // timing experiments only (AW_PERSISTENT_DEBUG)
+    bool eqFusion = false;         // AW_EQ_FUSION=1: steady-state EQ rides in KP's epilogue.  Off by default: the bit-exact float64
+                                   // recurrence needs ~220 cycles per sample, 29 us per 256-frame block on the few FFT warps of a
+                                   // CTA — longer than a tile lasts — whereas the separate K5 pass hides it behind 37 warps per SM
+                                   // (C4: 0.74 ms fused vs 0.54 ms separate)
     const float2 *d_tw = nullptr;
     float2 *d_fdl = nullptr;
     float *d_fdl_ny = nullptr, *d_overlap = nullptr, *d_pending = nullptr, *d_fifo = nullptr;
@@ -351,14 +355,34 @@ int eq_apply_pending_reset(aw_engine *e, EqMachine &m)   // :341-352
     return AW_OK;
 }
 
-// ParametricEqualizerProcessor.process (:254-314) for one machine, in place on `io`.
-int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
+// First half of ParametricEqualizerProcessor.process (:254-267): what the render thread does before it touches samples.
+int eq_begin_call(aw_engine *e, EqMachine &m)
 {
     if (!m.eqActive || !m.hasProcessor) return AW_OK;   // graph bypass / EqualizerRuntimeEffect passthrough
     int rc;
     if ((rc = eq_observe_published_target(e, m)) != AW_OK) return rc;
     if ((rc = eq_flush_pending_retirement(e, m)) != AW_OK) return rc;
-    if ((rc = eq_apply_pending_reset(e, m)) != AW_OK) return rc;
+    return eq_apply_pending_reset(e, m);
+}
+
+// Steady state (no crossfade) with a cascade the block kernel can fuse into its epilogue?
+bool eq_fusable(const aw_engine *e, const EqMachine &m, EqFuse *f)
+{
+    if (!m.eqActive || !m.hasProcessor || m.transitionFrom >= 0 || m.transitionTo >= 0) return false;
+    const int a = m.activeState;
+    if (!e->persistent || !persistent_can_fuse_eq(e->log2m, e->persistentTile, e->eqFilters[a])) return false;
+    f->prog = e->d_eq_prog + a;
+    f->z = e->d_eq_z;
+    f->voice = m.activeVoice;
+    f->n_filters = e->eqFilters[a];
+    return true;
+}
+
+// Second half of ParametricEqualizerProcessor.process (:269-314) for one machine, in place on `io`.
+int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
+{
+    if (!m.eqActive || !m.hasProcessor) return AW_OK;
+    int rc;
     int offset = 0;
     while (offset < frames) {
         EqLaunch l;
@@ -396,7 +420,7 @@ int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
 }
 
 // ---- one block of UPOLS for every rendering segment ----------------------------------------------------
-int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap, StridedOut out)
+int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap, StridedOut out, const EqFuse &eq)
 {
     for (Segment &seg : e->segments) {
         if (!seg.bank) continue;
@@ -418,7 +442,7 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
         if (e->persistent) {
             AW_LAUNCH(e, launch_persistent(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
-                                           e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, e->stream));
+                                           e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, eq, e->stream));
             if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
         } else if (e->fusedTile > 0) {
             // K2 + K3 + K4 in one kernel; events 0..1 bracket it, 1..3 collapse to zero-length intervals
@@ -450,6 +474,14 @@ int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, 
     if (frames <= 0) return AW_OK;                                              // :84
     if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");   // :85
     const int B = e->B;
+    const EqFuse no_eq{nullptr, nullptr, 0, 0};
+    // the equalizer's per-call bookkeeping (target observation, retirement, reset) does not depend on the samples: do it first,
+    // so that a steady-state cascade can ride in the block kernel's epilogue instead of a separate pass over the output
+    for (EqMachine &m : e->machines) {
+        const int rc = eq_begin_call(e, m);
+        if (rc != AW_OK) return rc;
+    }
+    EqFuse fused = no_eq;
     // streams without a published renderer: passthrough copy (HRIRManager.swift:555-564)
     for (const Segment &seg : e->segments)
         if (!seg.bank) AW_LAUNCH(e, launch_passthrough(in, out, seg.first, seg.count, dup_mono ? 1 : e->S, frames, e->stream));
@@ -460,12 +492,13 @@ int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, 
             // block-aligned fast path: same arithmetic, no pending/FIFO traffic (latency of one block is zero here
             // exactly as in the reference: B frames in -> processPendingBlock -> B frames drained in the same call)
             const int nb = frames / B;
+            if (e->eqFusion && e->segments.size() == 1 && e->machines.size() == 1) eq_fusable(e, e->machines[0], &fused);
             StridedIn ov{e->d_overlap, (long long)e->S * B, (long long)B};
             for (int b = 0; b < nb; ++b) {
                 StridedIn cur{in.ptr + (size_t)b * B, in.ss, in.cs};
                 StridedIn prev = b == 0 ? ov : StridedIn{in.ptr + (size_t)(b - 1) * B, in.ss, in.cs};
                 StridedOut o{out.ptr + (size_t)b * B, out.ss, out.cs, 0, 0};
-                const int rc = process_block(e, cur, prev, b == nb - 1, o);
+                const int rc = process_block(e, cur, prev, b == nb - 1, o, fused);
                 if (rc != AW_OK) return rc;
             }
         } else {
@@ -481,7 +514,7 @@ int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, 
                 if (e->pendingCount == B) {
                     const int writeIndex = (e->fifoReadIndex + e->fifoCount) % e->fifoCap;   // :167
                     StridedOut o{e->d_fifo, (long long)2 * e->fifoCap, (long long)e->fifoCap, e->fifoCap, writeIndex};
-                    const int rc = process_block(e, pend, ov, true, o);
+                    const int rc = process_block(e, pend, ov, true, o, no_eq);
                     if (rc != AW_OK) return rc;
                     e->fifoCount += B;
                     e->pendingCount = 0;
@@ -503,6 +536,7 @@ int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, 
     const bool prof = e->profOn && e->profEqUsed + 2 <= e->profEqEvents.size();
     if (prof) cudaEventRecord(e->profEqEvents[e->profEqUsed], e->stream);
     for (EqMachine &m : e->machines) {
+        if (fused.n_filters != 0) continue;              // already applied by the block kernel
         const int rc = eq_process_machine(e, m, out, frames);
         if (rc != AW_OK) return rc;
     }
@@ -861,6 +895,8 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         e->persistentCtas = c_env && atoi(c_env) > 0 ? atoi(c_env) : e->numSMs;
         const char *d_env = getenv("AW_PERSISTENT_DEBUG");
         e->persistentDebug = d_env ? atoi(d_env) : 0;
+        const char *q_env = getenv("AW_EQ_FUSION");
+        e->eqFusion = q_env && atoi(q_env) != 0;
         if (e->persistent) {
             // largest tile (most filter reuse) unless the smaller one loses clearly less to round quantisation
             auto eff = [&](int T) {

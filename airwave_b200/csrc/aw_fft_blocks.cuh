@@ -180,7 +180,8 @@ __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int
 // Inverse real FFT: the padded buffer holds the packed spectrum acc[0..M) (acc[0].x = DC) and ny the Nyquist value;
 // `emit(i, x0, x1)` receives the time samples x[2i], x[2i+1] for i in [M/2, M) — the overlap-save "second half".
 // All threads of the CTA must call it (barriers); `active` masks the stores only.
-template <int LOG2M, class Emit>
+// SYNC_BEFORE_EMIT: barrier between the last pass's loads and `emit`, for callers whose emit overwrites `buf`.
+template <int LOG2M, bool SYNC_BEFORE_EMIT = false, class Emit>
 __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float2 *tw, int t, bool active, Emit emit,
                                               GroupBar gb = GroupBar{0, 0})
 {
@@ -208,6 +209,7 @@ __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float
         constexpr int P = F::PASSES - 1;
         float2 v[F::E];
         smem_load<LOG2M, P>(buf, v, t);
+        if constexpr (SYNC_BEFORE_EMIT) group_sync<LOG2M>(gb);
         F::template compute<P>(v, tw, t);
         if (active) {
 #pragma unroll

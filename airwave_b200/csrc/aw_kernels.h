@@ -82,10 +82,18 @@ cudaError_t launch_fused(const BlockGeom &g, StridedIn cur, StridedIn prev, floa
 
 // KP: persistent warp-specialised block kernel (aw_persistent.cu): one CTA per SM, TMA bulk-copy ring, FFT warps one tile
 // ahead of the MAC warps; 64 <= B <= 2048.  `tile` = streams per tile (4 or 2).
+struct EqProgram;
+struct EqFuse {             // equalizer fused into KP's epilogue (steady state only); n_filters == 0: none
+    const EqProgram *prog;
+    double *z;              // [stream][voice(2)][ear(2)][filter(64)][2]
+    int voice;
+    int n_filters;          // 1..32
+};
+bool persistent_can_fuse_eq(int log2m, int tile, int n_filters);
 int persistent_tiles(int log2m);                // bit mask of the tiles available for that transform size (0 = unsupported)
 cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
                               const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
-                              int debug, cudaStream_t st);
+                              int debug, const EqFuse &eq, cudaStream_t st);
 
 size_t fft_smem_bytes(int log2m);
 cudaError_t configure_kernels(int log2m);   // opt in to > 48 KB dynamic shared memory for that transform size

@@ -94,6 +94,7 @@ struct PersistArgs {
     StridedOut out;
     const float2 *tw;
     int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms
+    EqFuse eq;   // steady-state equalizer applied to the block before it is stored (n_filters == 0: none)
 };
 
 template <int LOG2M, int T>
@@ -103,7 +104,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, RT = PG::RT, RS = PG::RS, CW = PG::CW, G = PG::G, NFT = PG::NFT;
     constexpr int STAGES = PG::STAGES, PS = PG::PS, stage_f4 = PG::stage_f4, PRODUCERS = PG::PRODUCERS;
     constexpr int MAC_WARPS = PG::MAC_THREADS / 32, SET_WARPS = 4, FFT_WARPS = PG::FFT_THREADS / 32;
-    constexpr int BAR_RED_A = 1, BAR_RED_B = 2, BAR_FFT0 = 4;
+    constexpr int BAR_RED_A = 1, BAR_RED_B = 2, BAR_EQ = 3, BAR_FFT0 = 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *ring = reinterpret_cast<float4 *>(smem_raw);
     float2 *tw = reinterpret_cast<float2 *>(smem_raw + (size_t)STAGES * PG::stage_bytes);
@@ -393,6 +394,18 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(heads_done)) : "memory");
         };
 
+        // fused equalizer (ParametricEqualizerState.process, ParametricEqualizerProcessor.swift:58-91): a systolic array across the
+        // lanes of a warp, lane f of a group of n_filters lanes owning biquad f of one (stream, ear) channel — see k_eq_systolic
+        const int gw = a.eq.n_filters;
+        const int eq_groups = gw > 0 ? 32 / gw : 0;
+        const int eg = gw > 0 ? lane / gw : 0, ef = gw > 0 ? lane - eg * gw : 0;
+        double eb0 = 0, eb1 = 0, eb2 = 0, ea1 = 0, ea2 = 0, epre = 1.0;
+        if (gw > 0 && eg < eq_groups) {
+            const double *cf = a.eq.prog->coef[ef];
+            eb0 = cf[0]; eb1 = cf[1]; eb2 = cf[2]; ea1 = cf[3]; ea2 = cf[4];
+            epre = a.eq.prog->preamp_linear;
+        }
+
         auto inverse_tile = [&](int lt) {
             const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
             const int nvalid = min(T, g.first_stream + g.n_streams - s0);
@@ -405,8 +418,48 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 // idle transforms of a working warp run on their (free) forward buffer so the warp stays converged
                 float2 *buf = idx < 2 * T ? accbuf + (size_t)idx * PS : fftbuf + (size_t)f * PS;
                 const float ny = nyquist_sum<G>(g, a.fdl_ny, a.bank_ny, stream, ear, active, t, my_part, gb);
-                float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
-                inverse_frame<LOG2M>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
+                if (gw == 0) {
+                    float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
+                    inverse_frame<LOG2M>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
+                } else {                                             // keep the block in shared memory (over the spectrum) for the EQ
+                    float *eb = reinterpret_cast<float *>(buf);
+                    inverse_frame<LOG2M, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { eb[2 * i] = x0; eb[2 * i + 1] = x1; }, gb);
+                }
+            }
+            if (gw > 0) {
+                named_sync(BAR_EQ, PG::FFT_THREADS);
+                const int fwarp = ft >> 5;
+                for (int ch0 = fwarp * eq_groups; ch0 < 2 * T; ch0 += FFT_WARPS * eq_groups) {   // warp-uniform
+                    const int ch = ch0 + eg;
+                    const bool live = eg < eq_groups && ch < 2 * T && (ch >> 1) < nvalid;
+                    float *eb = reinterpret_cast<float *>(accbuf + (size_t)(live ? ch : 0) * PS);
+                    double *zp = a.eq.z + ((((size_t)(s0 + (live ? ch >> 1 : 0)) * 2 + a.eq.voice) * 2 + (ch & 1)) * 64 + ef) * 2;
+                    double z1 = 0, z2 = 0, y = 0;
+                    if (live) { z1 = zp[0]; z2 = zp[1]; }
+                    for (int tt = 0; tt < M + gw - 1; ++tt) {
+                        const double up = __shfl_up_sync(0xffffffffu, y, 1);
+                        const int i = tt - ef;
+                        if (live && i >= 0 && i < M) {
+                            const double x = ef == 0 ? __dmul_rn((double)eb[i], epre) : up;   // preamp first (:66)
+                            y = __dadd_rn(__dmul_rn(eb0, x), z1);                                // no FMA contraction (:73-75)
+                            const double n1 = __dadd_rn(__dsub_rn(__dmul_rn(eb1, x), __dmul_rn(ea1, y)), z2);
+                            const double n2 = __dsub_rn(__dmul_rn(eb2, x), __dmul_rn(ea2, y));
+                            z1 = fabs(n1) < 1e-30 ? 0.0 : n1;                                    // :94-97
+                            z2 = fabs(n2) < 1e-30 ? 0.0 : n2;
+                            if (ef == gw - 1) eb[i] = (float)y;                                  // :88-89
+                        }
+                    }
+                    if (live) { zp[0] = z1; zp[1] = z2; }
+                }
+                named_sync(BAR_EQ, PG::FFT_THREADS);
+                for (int i = ft; i < 2 * T * (M / 2); i += PG::FFT_THREADS) {                    // coalesced store of the tile's block
+                    const int ch = i / (M / 2), j = i - ch * (M / 2);
+                    if ((ch >> 1) < nvalid) {
+                        const float *eb = reinterpret_cast<const float *>(accbuf + (size_t)ch * PS);
+                        float *row = a.out.ptr + (size_t)(s0 + (ch >> 1)) * a.out.ss + (ch & 1) * a.out.cs;
+                        store_pair(a.out, row, 2 * j, eb[2 * j], eb[2 * j + 1]);
+                    }
+                }
             }
         };
 
@@ -440,6 +493,14 @@ cudaError_t launch_persistent_lt(const PersistArgs &a, int ctas, cudaStream_t st
 
 }  // namespace
 
+// The fused equalizer runs on the FFT warps: fuse only when one systolic round covers the 2T channels of a tile.
+bool persistent_can_fuse_eq(int log2m, int tile, int n_filters)
+{
+    if (n_filters < 1 || n_filters > 32 || !(persistent_tiles(log2m) & tile)) return false;
+    const int G = (1 << log2m) / 16, fft_warps = (8 * G <= 128 ? 128 : 256) / 32;
+    return (32 / n_filters) * fft_warps >= 2 * tile;
+}
+
 // tiles supported for a transform size, as a bit mask of T
 int persistent_tiles(int log2m)
 {
@@ -450,11 +511,12 @@ int persistent_tiles(int log2m)
 
 cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
                               const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
-                              int debug, cudaStream_t st)
+                              int debug, const EqFuse &eq, cudaStream_t st)
 {
     if (g.n_streams <= 0) return cudaSuccess;
     if (!(persistent_tiles(g.log2m) & tile)) return cudaErrorInvalidValue;
-    PersistArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, bank, bank_ny, out, tw, debug};
+    if (eq.n_filters != 0 && (!persistent_can_fuse_eq(g.log2m, tile, eq.n_filters) || out.ring_cap > 0)) return cudaErrorInvalidValue;
+    PersistArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, bank, bank_ny, out, tw, debug, eq};
     const int tiles = (g.n_streams + tile - 1) / tile;
     const int ctas = tiles < max_ctas ? tiles : max_ctas;
 #define AW_KP(L, TT) return launch_persistent_lt<L, TT>(a, ctas, st)
