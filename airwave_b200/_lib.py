@@ -10,7 +10,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libairwave_cuda.so")
+# AW_LIBRARY: developer override to load an experimental build of the same library (kernel A/B tests); never a fallback
+LIB_PATH = os.environ.get("AW_LIBRARY") or os.path.join(HERE, "lib", "libairwave_cuda.so")
 HEADER_PATH = os.path.join(os.path.dirname(HERE), "include", "airwave_cuda.h")
 
 

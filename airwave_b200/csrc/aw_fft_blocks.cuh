@@ -112,7 +112,15 @@ __device__ __forceinline__ void group_sync(GroupBar gb = GroupBar{0, 0})
 }
 
 // Passes [P, LAST] entirely in shared memory (in place); every thread of the transform's group must call it.
-template <int LOG2M, int P, int LAST>
+// PT: `tw` is a per-pass twiddle table (RegFft::pt_entry layout) instead of the half-circle table.
+template <int LOG2M, int P, bool PT>
+__device__ __forceinline__ void pass_compute(float2 (&v)[RegFft<LOG2M>::E], const float2 *tw, int t)
+{
+    if constexpr (PT) RegFft<LOG2M>::template compute_pt<P>(v, tw, t);
+    else RegFft<LOG2M>::template compute<P>(v, tw, t);
+}
+
+template <int LOG2M, int P, int LAST, bool PT = false>
 struct SmemPasses {
     __device__ __forceinline__ static void run(float2 *buf, const float2 *tw, int t, GroupBar gb = GroupBar{0, 0})
     {
@@ -120,10 +128,10 @@ struct SmemPasses {
             float2 v[RegFft<LOG2M>::E];
             smem_load<LOG2M, P>(buf, v, t);
             group_sync<LOG2M>(gb);
-            RegFft<LOG2M>::template compute<P>(v, tw, t);
+            pass_compute<LOG2M, P, PT>(v, tw, t);
             smem_store<LOG2M, P>(buf, v, t);
             group_sync<LOG2M>(gb);
-            SmemPasses<LOG2M, P + 1, LAST>::run(buf, tw, t, gb);
+            SmemPasses<LOG2M, P + 1, LAST, PT>::run(buf, tw, t, gb);
         }
     }
 };
@@ -133,16 +141,16 @@ struct SmemPasses {
 // k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
 // Body of the forward real FFT of one frame whose pass-0 operands are already in registers (v[e] = z[load_index<0>(t, e)]):
 // lets a caller fetch the next frame from global memory while this one is being transformed.
-template <int LOG2M, class Emit, class EmitNy>
+template <int LOG2M, bool PT = false, class Emit, class EmitNy>
 __device__ __forceinline__ void forward_frame_regs(float2 *buf, const float2 *tw, int t, bool active, float2 (&v)[RegFft<LOG2M>::E],
                                                    Emit emit, EmitNy emit_ny, GroupBar gb = GroupBar{0, 0})
 {
     using F = RegFft<LOG2M>;
     constexpr int M = F::M;
-    F::template compute<0>(v, tw, t);
+    F::template compute<0>(v, tw, t);   // pass 0 has no twiddles
     smem_store<LOG2M, 0>(buf, v, t);
     group_sync<LOG2M>(gb);
-    SmemPasses<LOG2M, 1, F::PASSES - 1>::run(buf, tw, t, gb);
+    SmemPasses<LOG2M, 1, F::PASSES - 1, PT>::run(buf, tw, t, gb);
     if (active) {
         for (int k = t; k <= M / 2; k += F::G) {
             if (k == 0) {
@@ -166,7 +174,7 @@ __device__ __forceinline__ void forward_frame_regs(float2 *buf, const float2 *tw
 
 // Forward real FFT of one frame.  `load(i)` returns z[i] = x[2i] + i*x[2i+1] of the frame (i < M); `emit(k, X)` is called
 // by the owning threads for k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
-template <int LOG2M, class Load, class Emit, class EmitNy>
+template <int LOG2M, bool PT = false, class Load, class Emit, class EmitNy>
 __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int t, bool active, Load load, Emit emit, EmitNy emit_ny,
                                               GroupBar gb = GroupBar{0, 0})
 {
@@ -174,14 +182,14 @@ __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int
     float2 v[F::E];
 #pragma unroll
     for (int e = 0; e < F::E; ++e) v[e] = active ? load(F::template load_index<0>(t, e), e) : make_float2(0.f, 0.f);
-    forward_frame_regs<LOG2M>(buf, tw, t, active, v, emit, emit_ny, gb);
+    forward_frame_regs<LOG2M, PT>(buf, tw, t, active, v, emit, emit_ny, gb);
 }
 
 // Inverse real FFT: the padded buffer holds the packed spectrum acc[0..M) (acc[0].x = DC) and ny the Nyquist value;
 // `emit(i, x0, x1)` receives the time samples x[2i], x[2i+1] for i in [M/2, M) — the overlap-save "second half".
 // All threads of the CTA must call it (barriers); `active` masks the stores only.
 // SYNC_BEFORE_EMIT: barrier between the last pass's loads and `emit`, for callers whose emit overwrites `buf`.
-template <int LOG2M, bool SYNC_BEFORE_EMIT = false, class Emit>
+template <int LOG2M, bool SYNC_BEFORE_EMIT = false, bool PT = false, class Emit>
 __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float2 *tw, int t, bool active, Emit emit,
                                               GroupBar gb = GroupBar{0, 0})
 {
@@ -204,13 +212,13 @@ __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float
         }
     }
     group_sync<LOG2M>(gb);
-    SmemPasses<LOG2M, 0, F::PASSES - 2>::run(buf, tw, t, gb);
+    SmemPasses<LOG2M, 0, F::PASSES - 2, PT>::run(buf, tw, t, gb);
     {
         constexpr int P = F::PASSES - 1;
         float2 v[F::E];
         smem_load<LOG2M, P>(buf, v, t);
         if constexpr (SYNC_BEFORE_EMIT) group_sync<LOG2M>(gb);
-        F::template compute<P>(v, tw, t);
+        pass_compute<LOG2M, P, PT>(v, tw, t);
         if (active) {
 #pragma unroll
             for (int e = 0; e < F::E; ++e) {

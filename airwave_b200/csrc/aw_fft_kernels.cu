@@ -23,7 +23,8 @@ struct Geo {
     static constexpr int SA_THREADS = G > 128 ? G : 128;      // stand-alone K1/K2/K4
     static constexpr int SA_NF = SA_THREADS / G;
     static constexpr int PS = PaddedSize<LOG2M>::value;
-    static constexpr size_t sa_smem = (size_t)(M + SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
+    static constexpr int TW = pt_total_entries(LOG2M) > M ? pt_total_entries(LOG2M) : M;   // room for either twiddle layout
+    static constexpr size_t sa_smem = (size_t)(TW + SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -45,30 +46,34 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_input_rfft(const Inp
     constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufs = tw + M;
+    float2 *bufs = tw + Gm::TW;
     const int tid = threadIdx.x, f = tid / G, t = tid % G;
-    for (int k = tid; k < M; k += Gm::SA_THREADS) tw[k] = a.tw[k];
+    // per-pass twiddle tables (conflict-free reads), built once per CTA and amortised over the CTA's share of the frames
+    for (int k = tid; k < pt_total_entries(LOG2M); k += Gm::SA_THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     __syncthreads();
-    const int job = blockIdx.x * NF + f;
-    const bool active = job < a.g.n_streams * a.g.S;
-    const int ls = active ? job / a.g.S : 0, s = active ? job - ls * a.g.S : 0;
-    const int stream = a.g.first_stream + ls;
-    const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
-    const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
-    float *ov = a.overlap_save ? a.overlap_save + ((size_t)stream * a.g.Se + s) * M : nullptr;
-    const size_t row = ((size_t)stream * a.g.Se + s) * a.g.P_cap + a.g.head;
-    float2 *dst = a.fdl + row * M;
-    float *dst_ny = a.fdl_ny + row;
-    forward_frame<LOG2M>(
-        bufs + (size_t)f * Gm::PS, tw, t, active,
-        [&](int i, int) -> float2 {   // frame = [previous block | current block]  (:237-248)
-            if (i < M / 2) return *reinterpret_cast<const float2 *>(prev + 2 * i);
-            const float2 v = *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2));
-            if (ov) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v;   // inputOverlapBuffer <- current block (:243);
-            return v;                                                          // same thread read this address as `prev`
-        },
-        [&](int k, float2 x) { dst[k] = x; },       // FDL[head] <- spectrum (:256-264)
-        [&](float ny) { *dst_ny = ny; });
+    const int jobs = a.g.n_streams * a.g.S;
+    for (int base = blockIdx.x * NF; base < jobs; base += gridDim.x * NF) {   // uniform trip count: barriers inside
+        const int job = base + f;
+        const bool active = job < jobs;
+        const int ls = active ? job / a.g.S : 0, s = active ? job - ls * a.g.S : 0;
+        const int stream = a.g.first_stream + ls;
+        const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
+        const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
+        float *ov = a.overlap_save ? a.overlap_save + ((size_t)stream * a.g.Se + s) * M : nullptr;
+        const size_t row = ((size_t)stream * a.g.Se + s) * a.g.P_cap + a.g.head;
+        float2 *dst = a.fdl + row * M;
+        float *dst_ny = a.fdl_ny + row;
+        forward_frame<LOG2M, true>(
+            bufs + (size_t)f * Gm::PS, tw, t, active,
+            [&](int i, int) -> float2 {   // frame = [previous block | current block]  (:237-248)
+                if (i < M / 2) return *reinterpret_cast<const float2 *>(prev + 2 * i);
+                const float2 v = *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2));
+                if (ov) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v;   // inputOverlapBuffer <- current block (:243);
+                return v;                                                          // same thread read this address as `prev`
+            },
+            [&](int k, float2 x) { dst[k] = x; },       // FDL[head] <- spectrum (:256-264)
+            [&](float ny) { *dst_ny = ny; });
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -140,22 +145,26 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const Irff
     constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufs = tw + M;
+    float2 *bufs = tw + Gm::TW;
     float *part = reinterpret_cast<float *>(bufs + (size_t)NF * Gm::PS);
     const int tid = threadIdx.x, f = tid / G, t = tid % G;
-    for (int k = tid; k < M; k += Gm::SA_THREADS) tw[k] = a.tw[k];
-    const int job = blockIdx.x * NF + f;   // (local stream, ear)
-    const bool active = job < a.g.n_streams * 2;
-    const int stream = a.g.first_stream + (active ? job >> 1 : 0), ear = job & 1;
+    for (int k = tid; k < pt_total_entries(LOG2M); k += Gm::SA_THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     float2 *buf = bufs + (size_t)f * Gm::PS;
-    if (active) {
-        const float2 *src = a.acc + ((size_t)stream * 2 + ear) * M;
-        for (int k = t; k < M; k += G) buf[pad16(k)] = src[k];
+    const int jobs = a.g.n_streams * 2;   // (local stream, ear)
+    for (int base = blockIdx.x * NF; base < jobs; base += gridDim.x * NF) {   // uniform trip count: barriers inside
+        const int job = base + f;
+        const bool active = job < jobs;
+        const int stream = a.g.first_stream + (active ? job >> 1 : 0), ear = job & 1;
+        __syncthreads();                  // the previous round is done with buf (and the table is complete)
+        if (active) {
+            const float2 *src = a.acc + ((size_t)stream * 2 + ear) * M;
+            for (int k = t; k < M; k += G) buf[pad16(k)] = src[k];
+        }
+        __syncthreads();
+        const float ny = nyquist_sum<G>(a.g, a.fdl_ny, a.bank_ny, stream, ear, active, t, part + (size_t)f * G);
+        float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
+        inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
     }
-    __syncthreads();
-    const float ny = nyquist_sum<G>(a.g, a.fdl_ny, a.bank_ny, stream, ear, active, t, part + (size_t)f * G);
-    float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
-    inverse_frame<LOG2M>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -396,13 +405,28 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
     default: return cudaErrorInvalidValue;                                      \
     }
 
+// grid of the stand-alone transform kernels: every CTA loops over its share of the frames, so no more CTAs than can be resident
+// (227 KB of shared memory per SM, 148 SMs) — the twiddle tables are then built once per resident CTA instead of once per frame
+template <int LOG2M>
+static int sa_grid(int jobs)
+{
+    const int ctas = (jobs + Geo<LOG2M>::SA_NF - 1) / Geo<LOG2M>::SA_NF;
+    if (LOG2M <= 10) return ctas;   // measured: up to B = 1024 one frame group per CTA is faster (the CTA scheduler overlaps them)
+    int per_sm = (int)((227 * 1024) / (Geo<LOG2M>::sa_smem + 1024));
+    const int by_threads = 2048 / Geo<LOG2M>::SA_THREADS;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm < 1) per_sm = 1;
+    const int resident = 148 * per_sm;
+    return ctas < resident ? ctas : resident;
+}
+
 cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl,
                               float *fdl_ny, const float2 *tw, cudaStream_t st)
 {
     const int jobs = g.n_streams * g.S;
     if (jobs <= 0) return cudaSuccess;
     InputRfftArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, tw};
-#define CALL(L) k_input_rfft<L><<<(jobs + Geo<L>::SA_NF - 1) / Geo<L>::SA_NF, Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+#define CALL(L) k_input_rfft<L><<<sa_grid<L>(jobs), Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
     AW_LOG2M_SWITCH(g.log2m, CALL)
 #undef CALL
     return cudaGetLastError();
@@ -414,7 +438,7 @@ cudaError_t launch_irfft_out(const BlockGeom &g, const float2 *acc, const float 
     const int jobs = g.n_streams * 2;
     if (jobs <= 0) return cudaSuccess;
     IrfftArgs a{g, acc, fdl_ny, bank_ny, out, tw};
-#define CALL(L) k_irfft_out<L><<<(jobs + Geo<L>::SA_NF - 1) / Geo<L>::SA_NF, Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+#define CALL(L) k_irfft_out<L><<<sa_grid<L>(jobs), Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
     AW_LOG2M_SWITCH(g.log2m, CALL)
 #undef CALL
     return cudaGetLastError();

@@ -126,6 +126,19 @@ AW_HD constexpr int pass_log2r(int log2m, int p)
 AW_HD constexpr int pass_count(int log2m) { return pass_log2r(log2m, 3) ? 4 : pass_log2r(log2m, 2) ? 3 : pass_log2r(log2m, 1) ? 2 : 1; }
 AW_HD constexpr int pass_log2ns(int log2m, int p) { return p == 0 ? 0 : pass_log2ns(log2m, p - 1) + pass_log2r(log2m, p - 1); }
 
+// Per-pass twiddle tables ("PT" layout).  The half-circle table is read with strides that are powers of two (index
+// 2*r*k*M/(Ns*R) for the lanes' k), which serialises into up to 16 shared-memory wavefronts per load.  The PT layout stores, for
+// every pass with Ns > 1, the values that pass needs as [r-1][k] (k contiguous, so the lanes of a warp read consecutive
+// addresses): ptw[pass_tw_offset(P) + (r-1)*Ns + k] = w_M^(r*k*M/(Ns*R)).  A PT table starts with the M/2+1 entries the split
+// step reads (k contiguous already), padded to PT_SPLIT entries.
+AW_HD constexpr int pass_tw_entries(int log2m, int p) { return p == 0 ? 0 : ((1 << pass_log2r(log2m, p)) - 1) << pass_log2ns(log2m, p); }
+AW_HD constexpr int pass_tw_offset(int log2m, int p) { return p <= 1 ? 0 : pass_tw_offset(log2m, p - 1) + pass_tw_entries(log2m, p - 1); }
+AW_HD constexpr int pt_split_entries(int log2m) { return ((1 << log2m) / 2 + 1 + 15) & ~15; }
+AW_HD constexpr int pt_total_entries(int log2m)
+{
+    return pt_split_entries(log2m) + pass_tw_offset(log2m, pass_count(log2m) - 1) + pass_tw_entries(log2m, pass_count(log2m) - 1);
+}
+
 template <int LOG2M>
 struct RegFft {
     static constexpr int M = 1 << LOG2M;
@@ -176,6 +189,47 @@ struct RegFft {
             }
             Dft<R>::run(&v[q * R]);
         }
+    }
+    // same as compute<P>, twiddles from a PT table (pt = table base; the pass tables start at pt + pt_split_entries)
+    template <int P>
+    AW_HD static void compute_pt(float2 (&v)[E], const float2 *pt, int t)
+    {
+        constexpr int R = 1 << pass_log2r(LOG2M, P);
+        constexpr int Ns = 1 << pass_log2ns(LOG2M, P);
+        const float2 *tbl = pt + pt_split_entries(LOG2M) + pass_tw_offset(LOG2M, P);
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+        for (int q = 0; q < E / R; ++q) {
+            if (Ns > 1) {
+                const int k = (t + q * G) & (Ns - 1);
+#ifdef __CUDACC__
+#pragma unroll
+#endif
+                for (int r = 1; r < R; ++r) v[q * R + r] = cmul(v[q * R + r], tbl[(r - 1) * Ns + k]);
+            }
+            Dft<R>::run(&v[q * R]);
+        }
+    }
+    // entry i of the PT table from the half-circle table hc[k] = exp(-2*pi*i*k/(2M)), k < M
+    AW_HD static float2 pt_entry(const float2 *hc, int i)
+    {
+        if (i < pt_split_entries(LOG2M)) return hc[i < M ? i : M - 1];
+        i -= pt_split_entries(LOG2M);
+        float2 w = make_float2(1.f, 0.f);
+        for (int p = 1; p < PASSES; ++p) {
+            const int n = pass_tw_entries(LOG2M, p);
+            if (i < n) {
+                const int log2ns = pass_log2ns(LOG2M, p), log2r = pass_log2r(LOG2M, p);
+                const int r = 1 + (i >> log2ns), k = i & ((1 << log2ns) - 1);
+                const int i2 = 2 * r * (k * (M >> (log2ns + log2r)));
+                w = hc[i2 & (M - 1)];
+                if (i2 & M) { w.x = -w.x; w.y = -w.y; }
+                return w;
+            }
+            i -= n;
+        }
+        return w;
     }
 };
 

@@ -69,7 +69,8 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
     static constexpr int red_f4 = R > 1 ? (MAC_SETS * R - 1) * T * 2 * C : 0;   // partial sums of every (set, row) but the first
                                                                                  // (R == 1: exchanged through the accumulator buffers)
-    static constexpr size_t fixed_bytes = (size_t)M * sizeof(float2)                    // twiddles
+    static constexpr int TW = pt_total_entries(LOG2M);       // per-pass twiddle tables (conflict-free reads)
+    static constexpr size_t fixed_bytes = (size_t)TW * sizeof(float2)                   // twiddles
                                           + (size_t)(NFT + 2 * T) * PS * sizeof(float2)  // forward buffers + accumulator buffers
                                           + (size_t)red_f4 * sizeof(float4) + (size_t)FFT_THREADS * sizeof(float) + 1024;
     static constexpr int max_stages = (int)((226 * 1024 - fixed_bytes) / stage_bytes);
@@ -78,7 +79,10 @@ template <int LOG2M, int T> struct PGeo {
     // the sets alternating across the wrap.
     static constexpr int STAGES = (max_stages > 32 ? 32 : max_stages) / 2 * 2;
     static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
-    static constexpr bool PREFETCH = LOG2M <= 8;             // next round's operands fetched while this round transforms
+#ifndef AW_KP_PREFETCH_MAX
+#define AW_KP_PREFETCH_MAX 8
+#endif
+    static constexpr bool PREFETCH = LOG2M <= AW_KP_PREFETCH_MAX;   // next round's operands fetched while this round transforms
     static_assert(STAGES >= PRODUCERS && STAGES % MAC_SETS == 0, "ring geometry");
     static_assert(NC == 1 || RS == 1, "column chunks carry one row per stage");
 };
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float4 *ring = reinterpret_cast<float4 *>(smem_raw);
     float2 *tw = reinterpret_cast<float2 *>(smem_raw + (size_t)STAGES * PG::stage_bytes);
-    float2 *fftbuf = tw + M;
+    float2 *fftbuf = tw + PG::TW;
     float2 *accbuf = fftbuf + (size_t)NFT * PS;
     float4 *red = reinterpret_cast<float4 *>(accbuf + (size_t)2 * T * PS);
     float *part = reinterpret_cast<float *>(red + PG::red_f4);
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
     const int hs = (g.P - 1 + RS - 1) / RS;              // history stages per speaker (groups of RS partitions)
 
-    for (int k = tid; k < M; k += PG::THREADS) tw[k] = a.tw[k];
+    for (int k = tid; k < PG::TW; k += PG::THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], SET_WARPS); }
         *heads_done = 0;
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     const size_t row = ((size_t)stream * g.Se + sp) * g.P_cap + g.head;
                     float2 *dst = a.fdl + row * M;
                     float *dst_ny = a.fdl_ny + row;
-                    forward_frame_regs<LOG2M>(fftbuf + (size_t)f * PS, tw, t, active, v,
+                    forward_frame_regs<LOG2M, true>(fftbuf + (size_t)f * PS, tw, t, active, v,
                                               [&](int k, float2 x) { dst[k] = x; }, [&](float ny) { *dst_ny = ny; }, gb);   // FDL[head] <- spectrum (:256-264)
                 };
                 float2 v[F::E];
@@ -420,10 +424,10 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 const float ny = nyquist_sum<G>(g, a.fdl_ny, a.bank_ny, stream, ear, active, t, my_part, gb);
                 if (gw == 0) {
                     float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
-                    inverse_frame<LOG2M>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
+                    inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
                 } else {                                             // keep the block in shared memory (over the spectrum) for the EQ
                     float *eb = reinterpret_cast<float *>(buf);
-                    inverse_frame<LOG2M, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { eb[2 * i] = x0; eb[2 * i + 1] = x1; }, gb);
+                    inverse_frame<LOG2M, true, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { eb[2 * i] = x0; eb[2 * i + 1] = x1; }, gb);
                 }
             }
             if (gw > 0) {

@@ -8,6 +8,9 @@
 
 using namespace awfft;
 
+// `pt`: use the per-pass twiddle tables (RegFft::pt_entry layout, compute_pt) instead of the half-circle table
+static bool g_use_pt = false;
+
 template <int LOG2M, int P>
 struct RunPasses {
     static void run(std::vector<float2> &buf, const float2 *tw)
@@ -21,7 +24,8 @@ struct RunPasses {
         }
         for (int t = 0; t < F::G; ++t) {
             float2(&v)[F::E] = *reinterpret_cast<float2(*)[F::E]>(&regs[(size_t)t * F::E]);
-            F::template compute<(P < F::PASSES ? P : 0)>(v, tw, t);
+            if (g_use_pt) F::template compute_pt<(P < F::PASSES ? P : 0)>(v, tw, t);
+            else F::template compute<(P < F::PASSES ? P : 0)>(v, tw, t);
             PassRunner<LOG2M, (P < F::PASSES ? P : 0)>::store(buf.data(), v, t);
         }
         RunPasses<LOG2M, (P + 1 < 4 ? P + 1 : 4)>::run(buf, tw);
@@ -41,9 +45,13 @@ static void fft_one(const float *in, float *out)
     }
     std::vector<float2> buf(PaddedSize<LOG2M>::value);
     for (int i = 0; i < M; ++i) buf[pad16(i)] = make_float2(in[2 * i], in[2 * i + 1]);
-    RunPasses<LOG2M, 0>::run(buf, tw.data());
+    std::vector<float2> pt((size_t)pt_total_entries(LOG2M));
+    for (int i = 0; i < (int)pt.size(); ++i) pt[i] = RegFft<LOG2M>::pt_entry(tw.data(), i);
+    RunPasses<LOG2M, 0>::run(buf, g_use_pt ? pt.data() : tw.data());
     for (int i = 0; i < M; ++i) { out[2 * i] = buf[pad16(i)].x; out[2 * i + 1] = buf[pad16(i)].y; }
 }
+
+extern "C" void harness_regfft_use_pt(int on) { g_use_pt = on != 0; }
 
 extern "C" int harness_regfft(const float *in, int log2m, float *out)
 {

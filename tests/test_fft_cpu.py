@@ -47,6 +47,24 @@ def test_register_radix_fft_matches_numpy(regfft, log2m):
 
 
 @pytest.mark.parametrize("log2m", range(2, 14))
+def test_per_pass_twiddle_tables_give_bit_identical_transforms(regfft, log2m):
+    """compute_pt (conflict-free per-pass tables, used by the persistent kernel) reads the very same twiddle values as
+    compute (half-circle table): the transforms must agree bit for bit."""
+    M = 1 << log2m
+    rng = np.random.default_rng(200 + log2m)
+    inp = rng.uniform(-1, 1, (M, 2)).astype(np.float32)
+    a, b = np.zeros((M, 2), np.float32), np.zeros((M, 2), np.float32)
+    regfft.harness_regfft_use_pt(0)
+    assert regfft.harness_regfft(inp.ctypes.data_as(FP), log2m, a.ctypes.data_as(FP)) == 0
+    regfft.harness_regfft_use_pt(1)
+    try:
+        assert regfft.harness_regfft(inp.ctypes.data_as(FP), log2m, b.ctypes.data_as(FP)) == 0
+    finally:
+        regfft.harness_regfft_use_pt(0)
+    assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("log2m", range(2, 14))
 def test_real_fft_split_steps_match_numpy_and_round_trip(stockham, log2m):
     M, nf = 1 << log2m, 3
     N = 2 * M

@@ -246,3 +246,25 @@ def test_small_and_ragged_stream_counts_and_stereo_on_the_persistent_path(aw, hr
     for i in range(9):
         ref = oracle.direct_conv_f64(xu[i], hs)
         assert np.abs(y[i] - ref).max() <= MAX_ABS, i
+
+
+def test_fused_equalizer_epilogue_is_bit_identical_to_the_separate_pass(aw, hrtf_path, eq_fixture_bytes):
+    """AW_EQ_FUSION=1 (the cascade rides in the block kernel's epilogue) must not change a single bit: same operations in the
+    same order per biquad (ParametricEqualizerProcessor.swift:65-90), steady state after a finished crossfade included."""
+    definition = aw.EqualizerAPOParser.parse(eq_fixture_bytes, "f.txt")
+    outs = {}
+    for block, n in [(256, 37), (512, 9)]:
+        lay = aw.InputLayout.surround71()
+        bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), FS, lay, block)
+        x = oracle.synth_block(SEED, range(n), 8, 0, 16 * block)
+        for fusion in ("0", "1"):
+            os.environ["AW_EQ_FUSION"] = fusion
+            try:
+                eng = aw.BinauralEngine(n, 8, block, FS, max_frames_per_call=4 * block)
+            finally:
+                os.environ.pop("AW_EQ_FUSION", None)
+            eng.set_bank(bank)
+            eng.eq_prepare(definition)            # crossfade from unity over the first 960 frames, then steady state
+            outs[fusion] = np.concatenate([eng.process(x[:, :, a:a + 4 * block]) for a in range(0, 16 * block, 4 * block)], axis=2)
+            eng.close()
+        assert np.array_equal(outs["0"], outs["1"]), block
