@@ -97,7 +97,8 @@ struct PersistArgs {
     const float *bank_ny;
     StridedOut out;
     const float2 *tw;
-    int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms
+    int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms, bit 2 keeps the forward
+                 // transforms' arithmetic but not their memory traffic, bit 3 their traffic but not their arithmetic
     EqFuse eq;   // steady-state equalizer applied to the block before it is stored (n_filters == 0: none)
 };
 
@@ -350,11 +351,25 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
 #pragma unroll
                     for (int e = 0; e < F::E; ++e) {
                         const int i = F::template load_index<0>(t, e);   // frame = [previous block | current block] (:237-248)
-                        v[e] = !active ? make_float2(0.f, 0.f)
+                        v[e] = (!active || (a.debug & (4 | 32))) ? make_float2(0.f, 0.f)
                                        : (i < M / 2 ? *reinterpret_cast<const float2 *>(prev + 2 * i) : *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2)));
                     }
                 };
                 auto transform = [&](float2 (&v)[F::E], bool active, int stream, int sp) {
+                    if (a.debug & 8) {                   // timing experiment: the forward transform's memory traffic without its arithmetic
+                        if (active) {
+                            float2 *dst = a.fdl + (((size_t)stream * g.Se + sp) * g.P_cap + g.head) * M;
+#pragma unroll
+                            for (int e = 0; e < F::E; ++e) {
+                                const int i = F::template load_index<0>(t, e);
+                                dst[i] = v[e];
+                                if (a.overlap_save && i >= M / 2) *reinterpret_cast<float2 *>(a.overlap_save + ((size_t)stream * g.Se + sp) * M + 2 * (i - M / 2)) = v[e];
+                            }
+                        }
+                        return;
+                    }
+                    if (a.debug & (4 | 16)) active = false;   // timing experiments: 4 = arithmetic without traffic, 16 = loads but no stores,
+                                                                // 32 = stores but no loads
                     if (active && a.overlap_save) {   // inputOverlapBuffer <- current block (:243); this thread read the same addresses as `prev`
                         float *ov = a.overlap_save + ((size_t)stream * g.Se + sp) * M;
 #pragma unroll
