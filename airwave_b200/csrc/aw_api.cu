@@ -147,6 +147,11 @@ struct aw_engine {
     Staging stage[2];
     int nextStage = 0;
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
+    // engines whose stream ranges are bound to different banks (per-device profiles, DeviceProfileManager.swift:4-12) launch one
+    // grid per range; small ranges leave most SMs idle, so their grids are spread over side streams and run concurrently
+    static constexpr int kSideStreams = 8;
+    cudaStream_t side[kSideStreams] = {};
+    cudaEvent_t forkEvent = nullptr, joinEvent[kSideStreams] = {};
     std::vector<Segment> segments;
     std::vector<EqMachine> machines;
     // EQ state-object pool (host mirror of the programs resident on the device)
@@ -422,9 +427,21 @@ int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
 // ---- one block of UPOLS for every rendering segment ----------------------------------------------------
 int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap, StridedOut out, const EqFuse &eq)
 {
+    int rendering = 0;
+    for (const Segment &seg : e->segments) rendering += seg.bank != nullptr;
+    // several ranges: fork the block onto the side streams (round-robin), join before anything else touches the output
+    const bool fork = rendering >= 2 && !e->profOn && e->forkEvent != nullptr;
+    const int lanes = fork ? std::min(rendering, (int)aw_engine::kSideStreams) : 0;
+    if (fork) {
+        AW_CUDA(cudaEventRecord(e->forkEvent, e->stream));
+        for (int k = 0; k < lanes; ++k) AW_CUDA(cudaStreamWaitEvent(e->side[k], e->forkEvent, 0));
+    }
+    int ordinal = 0;
     for (Segment &seg : e->segments) {
         if (!seg.bank) continue;
         const aw_bank *b = seg.bank;
+        const cudaStream_t st = fork ? e->side[ordinal % lanes] : e->stream;
+        ++ordinal;
         seg.head -= 1;                                   // ConvolutionEngine.swift:256-259
         if (seg.head < 0) seg.head += b->P;
         BlockGeom g;
@@ -442,20 +459,26 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
         if (e->persistent) {
             AW_LAUNCH(e, launch_persistent(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
-                                           e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, eq, e->stream));
+                                           e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, eq, st));
             if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
         } else if (e->fusedTile > 0) {
             // K2 + K3 + K4 in one kernel; events 0..1 bracket it, 1..3 collapse to zero-length intervals
             AW_LAUNCH(e, launch_fused(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
-                                      e->d_tw, e->fusedTile, e->stream));
+                                      e->d_tw, e->fusedTile, st));
             if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
         } else {
-            AW_LAUNCH(e, launch_input_rfft(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, e->d_tw, e->stream));
+            AW_LAUNCH(e, launch_input_rfft(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, e->d_tw, st));
             if (prof) cudaEventRecord(ev[1], e->stream);
-            AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, b->d_bank, e->d_acc, e->macTile, e->stream));
+            AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, b->d_bank, e->d_acc, e->macTile, st));
             if (prof) cudaEventRecord(ev[2], e->stream);
-            AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, b->d_ny, out, e->d_tw, e->stream));
+            AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, b->d_ny, out, e->d_tw, st));
             if (prof) cudaEventRecord(ev[3], e->stream);
+        }
+    }
+    if (fork) {
+        for (int k = 0; k < lanes; ++k) {
+            AW_CUDA(cudaEventRecord(e->joinEvent[k], e->side[k]));
+            AW_CUDA(cudaStreamWaitEvent(e->stream, e->joinEvent[k], 0));
         }
     }
     ++e->blocks;
@@ -559,6 +582,11 @@ void free_engine(aw_engine *e)
     }
     for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->profEqEvents) cudaEventDestroy(ev);
+    for (int k = 0; k < aw_engine::kSideStreams; ++k) {
+        if (e->side[k]) cudaStreamDestroy(e->side[k]);
+        if (e->joinEvent[k]) cudaEventDestroy(e->joinEvent[k]);
+    }
+    if (e->forkEvent) cudaEventDestroy(e->forkEvent);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
     if (e->d2h) cudaStreamDestroy(e->d2h);
@@ -834,6 +862,11 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
     AW_TRY(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     AW_TRY(cudaStreamCreateWithFlags(&e->h2d, cudaStreamNonBlocking));
     AW_TRY(cudaStreamCreateWithFlags(&e->d2h, cudaStreamNonBlocking));
+    for (int k = 0; k < aw_engine::kSideStreams; ++k) {
+        AW_TRY(cudaStreamCreateWithFlags(&e->side[k], cudaStreamNonBlocking));
+        AW_TRY(cudaEventCreateWithFlags(&e->joinEvent[k], cudaEventDisableTiming));
+    }
+    AW_TRY(cudaEventCreateWithFlags(&e->forkEvent, cudaEventDisableTiming));
     const size_t n = e->n, S = e->S, B = e->B;
     AW_TRY(cudaMalloc(&e->d_overlap, n * S * B * sizeof(float)));
     AW_TRY(cudaMalloc(&e->d_pending, n * S * B * sizeof(float)));

@@ -44,6 +44,8 @@ WORKLOADS = {
     "C3": ("7.1->binaural, synthetic 65,536-tap BRIR, B=512, 1024 streams/GPU", 8, 512, 1024, "synthetic65536"),
     "C4": ("full chain: 7.1->binaural with StageSH1.0 relabelled 44.1 kHz and resampled to 48 kHz (4320 -> 4702 taps), B=256, "
            "+ 10-band parametric EQ (CCA CRA fixture), 8192 streams/GPU", 8, 256, 8192, "StageSH1.0@44100"),
+    "F3": ("per-device profiles at batch scale (SURVEY.md 8(f3)): 4096 streams in 64 ranges bound alternately to the RoomSH1.0 and "
+           "StageSH1.0 banks, 7.1->binaural, B=256", 8, 256, 4096, "RoomSH1.0+StageSH1.0"),
     "C5-64": ("7.1->binaural, RoomSH1.0, B=64, 2048 streams/GPU", 8, 64, 2048, "RoomSH1.0"),
     "C5-128": ("7.1->binaural, RoomSH1.0, B=128, 2048 streams/GPU", 8, 128, 2048, "RoomSH1.0"),
     "C5-512": ("7.1->binaural, RoomSH1.0, B=512, 2048 streams/GPU", 8, 512, 2048, "RoomSH1.0"),
@@ -191,7 +193,7 @@ def run_reference(args):
     import numpy as np
     import oracle
     desc, S, B, n_per_gpu, hrir = WORKLOADS[args.workload]
-    pcm, rate = hrir_pcm_cpu(hrir)
+    pcm, rate = hrir_pcm_cpu(hrir.split("+")[0])
     l_idx, r_idx = hesuvi14_cpu(S)
     h = cpu_filters(S, pcm, rate, l_idx, r_idx)
     taps = h.shape[2]
@@ -277,13 +279,21 @@ def run_ours(args):
     desc, S, B, n, hrir = WORKLOADS[args.workload]
     if args.streams > 0:
         n = args.streams
-    pcm, rate = hrir_pcm(hrir)
+    presets = hrir.split("+")
+    pcm, rate = hrir_pcm(presets[0])
     l_idx, r_idx = speaker_maps(S)
     bank = aw.HRIRBank(pcm, rate, FS, l_idx, r_idx, B, device=local)
+    banks = [bank] + [aw.HRIRBank(*hrir_pcm(name), FS, l_idx, r_idx, B, device=local) for name in presets[1:]]
     P, taps = bank.partitions, bank.taps
     e2e_frames = max(B, min(4096, args.e2e_frames // B * B))
     eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=e2e_frames, max_partitions=P, device=local, pipelined=True)
-    eng.set_bank(bank)
+    if len(banks) == 1:
+        eng.set_bank(bank)
+    else:                                     # 64 ranges, banks alternating: one grid per range, run concurrently on side streams
+        ranges = 64
+        per = n // ranges
+        for r in range(ranges):
+            eng.set_bank(banks[r % len(banks)], r * per, per if r < ranges - 1 else n - r * per)
     eq_def = eq_definition_for(args.workload, aw.EqualizerAPOParser.parse)
     eq_filters = 0
     if eq_def is not None:                    # full chain: spatial -> EQ (AudioEffectGraph.swift:195-210)
@@ -385,7 +395,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample = cpu_sample(S, B, pcm, rate, l_idx, r_idx, args.cpu_seconds)
+        v, cores, sample = cpu_sample(S, B, pcm, rate, l_idx, r_idx, args.cpu_seconds)   # (first bank of the workload)
         if eq_def is not None:
             sample += "; convolution only (the EQ cascade is not part of the CPU sample)"
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}

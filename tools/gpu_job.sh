@@ -1,4 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-BENCH_ENV="AW_PERSISTENT_DEBUG=16" bash tools/bench_all.sh C5-512 C2
-BENCH_ENV="AW_PERSISTENT_DEBUG=32" bash tools/bench_all.sh C5-512 C2
+timeout 900 python -m pytest tests/test_gpu_fullsize.py tests/test_gpu_convolution.py -m gpu -x -q -k "many_profile or per_range or independent" --timeout 600 2>&1 | tail -3
+bash tools/bench_all.sh F3 C2
