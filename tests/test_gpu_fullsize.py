@@ -294,3 +294,22 @@ def test_many_profile_ranges_render_concurrently_and_match_single_bank_engines(a
         for r in range(b, ranges, 3):
             for i in range(bounds[r], bounds[r + 1]):
                 assert np.array_equal(y[i], yr[i % 40]), (r, i)
+
+
+def test_bank_with_fewer_speakers_than_the_engine_has_channels(aw, hrtf_path):
+    """A 5.1 bank on an engine laid out for 8 input channels (state arrays strided by the engine's channel count, renderers =
+    the bank's speakers, RealtimeAudioProcessor.swift:145-147): channels 6 and 7 are ignored and the result is bit-identical
+    to a 6-channel engine fed the first 6 channels."""
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), FS, aw.InputLayout.surround51(), 256)
+    n = 11
+    x = oracle.synth_block(SEED, range(n), 8, 0, 24 * 256)
+    wide = aw.BinauralEngine(n, 8, 256, FS, max_frames_per_call=1024, max_partitions=17)
+    wide.set_bank(bank)
+    narrow = aw.BinauralEngine(n, 6, 256, FS, max_frames_per_call=1024, max_partitions=17)
+    narrow.set_bank(bank)
+    yw = np.concatenate([wide.process(x[:, :, a:a + 1024]) for a in range(0, 24 * 256, 1024)], axis=2)
+    yn = np.concatenate([narrow.process(np.ascontiguousarray(x[:, :6, a:a + 1024])) for a in range(0, 24 * 256, 1024)], axis=2)
+    assert np.array_equal(yw, yn)
+    h = oracle.hrir_matrix(oracle.load_wav(hrtf_path("RoomSH1.0")), FS, oracle.InputLayout.surround51)
+    ref = oracle.direct_conv_f64(x[3, :6], h)
+    assert np.abs(yw[3] - ref).max() <= MAX_ABS and snr_db(ref, yw[3]) >= SNR_DB
