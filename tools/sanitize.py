@@ -1,0 +1,30 @@
+"""GPU-side helper: a few small renders through every execution path, meant to be run under compute-sanitizer
+(memcheck / synccheck / initcheck).  usage: compute-sanitizer --tool memcheck python tools/sanitize.py"""
+import os, sys
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import airwave_b200 as aw
+
+FS = 48000.0
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+wav = aw.WAVLoader.load(os.path.join(root, "tests", "golden", "hrtf", "RoomSH1.0.wav"))
+eqtxt = open(os.path.join(root, "tests", "golden", "eq", "CCA CRA ParametricEq.txt"), "rb").read()
+definition = aw.EqualizerAPOParser.parse(eqtxt, "f")
+rng = np.random.default_rng(0)
+for block, n, env in [(64, 9, {}), (128, 9, {}), (256, 21, {}), (512, 9, {}), (1024, 5, {}), (2048, 3, {}), (4096, 2, {}),
+                      (256, 9, {"AW_PERSISTENT": "0"}), (256, 9, {"AW_FUSED_TILE": "0"}), (256, 9, {"AW_EQ_FUSION": "1"}),
+                      (256, 13, {"AW_PERSISTENT_CTAS": "2"}), (256, 700, {}), (512, 650, {}), (64, 640, {}), (1024, 301, {"AW_PERSISTENT_TILE": "4"})]:
+    os.environ.update(env)
+    bank = aw.HRIRBank.from_wav(wav, FS, aw.InputLayout.surround71(), block)
+    eng = aw.BinauralEngine(n, 8, block, FS, max_frames_per_call=min(4096, 2 * block))
+    for k in env:
+        os.environ.pop(k)
+    eng.set_bank(bank)
+    eng.eq_prepare(definition)
+    for call in range(3):
+        x = rng.uniform(-0.25, 0.25, (n, 8, min(4096, 2 * block))).astype(np.float32)
+        y = eng.process(x)
+    y = eng.process(x[:, :, :37])          # ragged call: adapter path
+    assert np.isfinite(y).all()
+    print("ok", block, n, env, eng.plan()["kernels"], flush=True)
+    eng.close()
