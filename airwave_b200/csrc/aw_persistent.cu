@@ -14,12 +14,12 @@
 //                       R FDL rows of a stream are consecutive ring slots, so they travel as one copy (two at the wrap).
 //                       Rows wider than 128 bin pairs are walked in column chunks (accumulators stay in registers for the
 //                       whole chunk).
-//   8 MAC warps         two sets of 128 threads that take alternate stages; a thread owns one bin pair (two complex bins, one
+//   8 MAC warps         (4 from B = 1024) two sets of 128 threads that take alternate stages; a thread owns one bin pair (two complex bins, one
 //                       float4 of FDL) of one row of the stage for ALL T streams and both ears, so a filter value is read
 //                       from shared memory once per T streams (shared-memory bandwidth is the resource next to HBM here).
 //                       full/empty mbarriers per stage.  The partial sums of the sets (and of the R rows) are reduced
 //                       through shared memory in a fixed order (deterministic).
-//   4 or 8 FFT warps    run the forward transforms ONE TILE AHEAD of the MAC warps (nothing but the head slot of the FDL
+//   4, 8 or 12 FFT warps  run the forward transforms ONE TILE AHEAD of the MAC warps (nothing but the head slot of the FDL
 //                       depends on them), and the inverse transforms of the tile the MAC warps just finished
 //                       (accumulators handed over through shared memory, acc_ready/acc_free mbarriers).
 //
@@ -46,10 +46,12 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int R = C < 128 ? 128 / C : 1;          // rows side by side in a MAC set (one per C threads)
     static constexpr int RT = LOG2M <= 8 ? 2 : 1;            // rows per MAC thread
     static constexpr int RS = R * RT;                        // rows ((speaker, partition) pairs, consecutive partitions) per stage
-    static constexpr int MAC_SETS = 2;                       // sets of 128 MAC threads; set q drains the ring slots of parity q
+    // sets of 128 MAC threads; set q drains the ring slots q, q + MAC_SETS, ...  From B = 1024 the transforms, not the MAC, set the
+    // pace (P is small, 10 transforms of 2B points per stream and block): one MAC set, and the threads go to the FFT warps.
+    static constexpr int MAC_SETS = LOG2M >= 10 ? 1 : 2;
     static constexpr int MAC_THREADS = MAC_SETS * 128;
     static constexpr int G = RegFft<LOG2M>::G;               // threads per transform
-    static constexpr int FFT_THREADS = 8 * G <= 128 ? 128 : 256;
+    static constexpr int FFT_THREADS = LOG2M >= 10 ? 384 : (8 * G <= 128 ? 128 : 256);
     static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
     // producer warps, one issuing lane each.  B >= 512 with T = 4: three, so that the 19 warps get 104 registers each (the MAC
     // threads hold 2 bin pairs x 4 streams x 2 ears of accumulators); at B = 512 the 6 ring slots divide evenly among them.
@@ -75,15 +77,15 @@ template <int LOG2M, int T> struct PGeo {
                                           + (size_t)red_f4 * sizeof(float4) + (size_t)FFT_THREADS * sizeof(float) + 1024;
     static constexpr int max_stages = (int)((226 * 1024 - fixed_bytes) / stage_bytes);
     // A ring slot is always filled by the same producer warp (slot index mod PRODUCERS) and drained by the same MAC set (slot
-    // index mod 2): mbarrier parity waits are only safe for a waiter that is at most one phase behind.  Even depth keeps
-    // the sets alternating across the wrap.
+    // index mod MAC_SETS): mbarrier parity waits are only safe for a waiter that is at most one phase behind.  Even depth keeps
+    // two sets alternating across the wrap.
     static constexpr int STAGES = (max_stages > 32 ? 32 : max_stages) / 2 * 2;
     static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
 #ifndef AW_KP_PREFETCH_MAX
 #define AW_KP_PREFETCH_MAX 8
 #endif
     static constexpr bool PREFETCH = LOG2M <= AW_KP_PREFETCH_MAX;   // next round's operands fetched while this round transforms
-    static_assert(STAGES >= PRODUCERS && STAGES % MAC_SETS == 0, "ring geometry");
+    static_assert(STAGES >= PRODUCERS && STAGES % MAC_SETS == 0 && (MAC_SETS == 2 || R == 1), "ring geometry");
     static_assert(NC == 1 || RS == 1, "column chunks carry one row per stage");
 };
 
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         unsigned phase = 0;
         int m = set;                                         // my next stage, relative to the current chunk
         int jj = hs > 0 ? set % hs : 0;                      // its history group (RS > 1 only)
+        constexpr int SETS = PG::MAC_SETS;
         for (int lt = 0; lt < my_tiles; ++lt) {
             for (int c = 0; c < NC; ++c) {
                 float4 aL[CW][T], aR[CW][T];
@@ -221,7 +224,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 for (int v = 0; v < CW; ++v)
 #pragma unroll
                     for (int u = 0; u < T; ++u) { aL[v][u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[v][u] = aL[v][u]; }
-                for (; m < spc; m += 2) {
+                for (; m < spc; m += SETS) {
                     int nrows = 1;                           // head stages carry one row
                     if (RS > 1 && m < head0) nrows = min(RS, g.P - 1 - jj * RS);
                     mbar_wait(&full[stage], phase);
@@ -247,15 +250,28 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     }
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty[stage]);
-                    stage += 2;
+                    stage += SETS;
                     if (stage >= STAGES) { stage -= STAGES; phase ^= 1u; }
-                    if (RS > 1 && hs > 0) { jj += 2; while (jj >= hs) jj -= hs; }
+                    if (RS > 1 && hs > 0) { jj += SETS; while (jj >= hs) jj -= hs; }
                 }
                 m -= spc;                                    // position in the next chunk
                 if (RS > 1) jj = hs > 0 ? m % hs : 0;
                 // the FFT warps must be done with the previous tile's accumulators before they are overwritten
                 if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
-                if constexpr (R == 1) {
+                if constexpr (R == 1 && SETS == 1) {
+#pragma unroll
+                    for (int v = 0; v < CW; ++v) {
+                        const int J = c * C + jp + 128 * v;          // bins 2J, 2J+1
+#pragma unroll
+                        for (int u = 0; u < T; ++u) {
+                            float2 *bl = accbuf + (size_t)(2 * u) * PS, *br = bl + PS;
+                            bl[pad16(2 * J)] = make_float2(aL[v][u].x, aL[v][u].y);
+                            bl[pad16(2 * J + 1)] = make_float2(aL[v][u].z, aL[v][u].w);
+                            br[pad16(2 * J)] = make_float2(aR[v][u].x, aR[v][u].y);
+                            br[pad16(2 * J + 1)] = make_float2(aR[v][u].z, aR[v][u].w);
+                        }
+                    }
+                } else if constexpr (R == 1) {
                     // set 1 hands its partial sums over in the accumulator buffers; set 0 adds its own and leaves the result there
                     if (set == 1) {
 #pragma unroll
@@ -523,8 +539,8 @@ bool persistent_can_fuse_eq(int log2m, int tile, int n_filters)
 // tiles supported for a transform size, as a bit mask of T
 int persistent_tiles(int log2m)
 {
-    if (log2m >= 6 && log2m <= 10) return 4 | 2;
-    if (log2m == 11) return 2;
+    if (log2m >= 6 && log2m <= 9) return 4 | 2;
+    if (log2m == 10 || log2m == 11) return 2;   // the transform buffers of 12 FFT warps leave no room for a T = 4 ring
     return 0;
 }
 
@@ -545,7 +561,6 @@ cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev,
         case 7: AW_KP(7, 4);
         case 8: AW_KP(8, 4);
         case 9: AW_KP(9, 4);
-        case 10: AW_KP(10, 4);
         default: return cudaErrorInvalidValue;
         }
     }

@@ -178,10 +178,10 @@ def test_c5_block_size_sweep_2048_streams(aw, hrtf_path, block):
 
 
 PATHS = [  # (name, env, block sizes it exists for)
-    ("persistent T=4", {"AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512, 1024)),
+    ("persistent T=4", {"AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512)),
     ("persistent T=2", {"AW_PERSISTENT_TILE": "2"}, (64, 128, 256, 512, 1024, 2048)),
     ("persistent T=2, 3 CTAs", {"AW_PERSISTENT_CTAS": "3", "AW_PERSISTENT_TILE": "2"}, (64, 128, 256, 512, 1024, 2048)),
-    ("persistent T=4, 2 CTAs", {"AW_PERSISTENT_CTAS": "2", "AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512, 1024)),
+    ("persistent T=4, 2 CTAs", {"AW_PERSISTENT_CTAS": "2", "AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512)),
     ("fused", {"AW_PERSISTENT": "0"}, (64, 128, 256, 512)),
     ("split", {"AW_FUSED_TILE": "0"}, (64, 128, 256, 512, 1024, 2048)),
 ]

@@ -13,7 +13,7 @@ definition = aw.EqualizerAPOParser.parse(eqtxt, "f")
 rng = np.random.default_rng(0)
 for block, n, env in [(64, 9, {}), (128, 9, {}), (256, 21, {}), (512, 9, {}), (1024, 5, {}), (2048, 3, {}), (4096, 2, {}),
                       (256, 9, {"AW_PERSISTENT": "0"}), (256, 9, {"AW_FUSED_TILE": "0"}), (256, 9, {"AW_EQ_FUSION": "1"}),
-                      (256, 13, {"AW_PERSISTENT_CTAS": "2"}), (256, 700, {}), (512, 650, {}), (64, 640, {}), (1024, 301, {"AW_PERSISTENT_TILE": "4"})]:
+                      (256, 13, {"AW_PERSISTENT_CTAS": "2"}), (256, 700, {}), (512, 650, {}), (64, 640, {}), (1024, 301, {})]:
     os.environ.update(env)
     bank = aw.HRIRBank.from_wav(wav, FS, aw.InputLayout.surround71(), block)
     eng = aw.BinauralEngine(n, 8, block, FS, max_frames_per_call=min(4096, 2 * block))
