@@ -427,9 +427,46 @@ int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
 // ---- one block of UPOLS for every rendering segment ----------------------------------------------------
 int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap, StridedOut out, const EqFuse &eq)
 {
+    for (Segment &seg : e->segments) {
+        if (!seg.bank) continue;
+        seg.head -= 1;                                   // ConvolutionEngine.swift:256-259
+        if (seg.head < 0) seg.head += seg.bank->P;
+    }
+    const bool literal = (e->cfg.flags & AW_ENGINE_LITERAL_STEREO) != 0;   // RealtimeAudioProcessor.swift:145
+    if (e->persistent) {
+        // KP: ONE launch walks the tiles of every range (up to kKpMaxSegments per launch), whatever bank each is bound to
+        KpSegment segs[kKpMaxSegments];
+        size_t i = 0;
+        while (i < e->segments.size()) {
+            int n = 0;
+            for (; i < e->segments.size() && n < kKpMaxSegments; ++i) {
+                const Segment &seg = e->segments[i];
+                if (!seg.bank) continue;
+                KpSegment &k = segs[n++];
+                k.first_stream = seg.first;
+                k.n_streams = seg.count;
+                k.S = literal ? std::min(seg.bank->S, 2) : seg.bank->S;
+                k.P = seg.bank->P;
+                k.head = seg.head;
+                k.tile0 = 0;
+                k.bank = seg.bank->d_bank;
+                k.bank_ny = seg.bank->d_ny;
+            }
+            if (n == 0) break;
+            const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
+            cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
+            if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
+            AW_LAUNCH(e, launch_persistent(segs, n, e->S, e->P_cap, e->log2m, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl,
+                                           e->d_fdl_ny, out, e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, eq, e->stream));
+            if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
+        }
+        ++e->blocks;
+        return AW_OK;
+    }
     int rendering = 0;
     for (const Segment &seg : e->segments) rendering += seg.bank != nullptr;
-    // several ranges: fork the block onto the side streams (round-robin), join before anything else touches the output
+    // KF / split kernels, several ranges: fork the block onto the side streams (round-robin), join before anything else touches
+    // the output
     const bool fork = rendering >= 2 && !e->profOn && e->forkEvent != nullptr;
     const int lanes = fork ? std::min(rendering, (int)aw_engine::kSideStreams) : 0;
     if (fork) {
@@ -442,12 +479,10 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         const aw_bank *b = seg.bank;
         const cudaStream_t st = fork ? e->side[ordinal % lanes] : e->stream;
         ++ordinal;
-        seg.head -= 1;                                   // ConvolutionEngine.swift:256-259
-        if (seg.head < 0) seg.head += b->P;
         BlockGeom g;
         g.first_stream = seg.first;
         g.n_streams = seg.count;
-        g.S = (e->cfg.flags & AW_ENGINE_LITERAL_STEREO) ? std::min(b->S, 2) : b->S;   // RealtimeAudioProcessor.swift:145
+        g.S = literal ? std::min(b->S, 2) : b->S;
         g.Se = e->S;
         g.B = e->B;
         g.log2m = e->log2m;
@@ -457,11 +492,7 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
         cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
         if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
-        if (e->persistent) {
-            AW_LAUNCH(e, launch_persistent(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
-                                           e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, eq, st));
-            if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
-        } else if (e->fusedTile > 0) {
+        if (e->fusedTile > 0) {
             // K2 + K3 + K4 in one kernel; events 0..1 bracket it, 1..3 collapse to zero-length intervals
             AW_LAUNCH(e, launch_fused(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
                                       e->d_tw, e->fusedTile, st));

@@ -91,8 +91,16 @@ struct EqFuse {             // equalizer fused into KP's epilogue (steady state 
 };
 bool persistent_can_fuse_eq(int log2m, int tile, int n_filters);
 int persistent_tiles(int log2m);                // bit mask of the tiles available for that transform size (0 = unsupported)
-cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
-                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
+struct KpSegment {          // a stream range bound to one bank (tile0 is filled in by the launcher)
+    int first_stream, n_streams;
+    int S, P, head;         // renderers, partitions (ring modulus), fdlIndex after this block's decrement
+    int tile0;
+    const float4 *bank;
+    const float *bank_ny;
+};
+constexpr int kKpMaxSegments = 64;   // per launch (64 x 40 B of the 4 KB kernel parameter space)
+cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_cap, int log2m, StridedIn cur, StridedIn prev,
+                              float *overlap_save, float2 *fdl, float *fdl_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
                               int debug, const EqFuse &eq, cudaStream_t st);
 
 size_t fft_smem_bytes(int log2m);

@@ -28,6 +28,8 @@
 // Stage order inside a tile (and column chunk): for every speaker its history partitions p = 1..P-1 in groups of R, then
 // the S head rows — the same for every tile size and stream count, so a stream's output does not depend on how many
 // streams the engine renders or on which GPU it lives.
+#include <string.h>
+
 #include "aw_fft_blocks.cuh"
 
 namespace aw {
@@ -89,14 +91,16 @@ template <int LOG2M, int T> struct PGeo {
     static_assert(NC == 1 || RS == 1, "column chunks carry one row per stage");
 };
 
+// One launch serves up to kMaxSegs stream ranges ("segments": streams bound to the same bank — per-device profiles,
+// DeviceProfileManager.swift:4-12).  Tiles are numbered across the segments; a tile never straddles two of them.
 struct PersistArgs {
-    BlockGeom g;
+    int n_segs, n_tiles;
+    int Se, P_cap;               // engine-wide layout of the state arrays (speakers per stream, FDL slots per (stream, speaker))
+    KpSegment seg[kKpMaxSegments];
     StridedIn cur, prev;
     float *overlap_save;
     float2 *fdl;
     float *fdl_ny;
-    const float4 *bank;
-    const float *bank_ny;
     StridedOut out;
     const float2 *tw;
     int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms, bit 2 keeps the forward
@@ -104,8 +108,31 @@ struct PersistArgs {
     EqFuse eq;   // steady-state equalizer applied to the block before it is stored (n_filters == 0: none)
 };
 
+struct TileCtx {                 // what a role needs to know about the tile it works on
+    int s0, nvalid, last;        // first stream, valid streams (< T in a segment's last tile), last stream of the segment
+    int S, P, head, hs;          // renderers, partitions, FDL head slot, history stages per speaker
+    const float4 *bank;
+    const float *bank_ny;
+};
+
+template <int T, int RS>
+__device__ __forceinline__ TileCtx tile_ctx(const PersistArgs &a, int tile)
+{
+    int i = 0;
+    while (i + 1 < a.n_segs && tile >= a.seg[i + 1].tile0) ++i;
+    const KpSegment &d = a.seg[i];
+    TileCtx c;
+    c.s0 = d.first_stream + (tile - d.tile0) * T;
+    c.last = d.first_stream + d.n_streams - 1;
+    c.nvalid = min(T, c.last + 1 - c.s0);
+    c.S = d.S; c.P = d.P; c.head = d.head;
+    c.hs = (d.P - 1 + RS - 1) / RS;
+    c.bank = d.bank; c.bank_ny = d.bank_ny;
+    return c;
+}
+
 template <int LOG2M, int T>
-__global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const PersistArgs a)
+__global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const __grid_constant__ PersistArgs a)
 {
     using PG = PGeo<LOG2M, T>;
     constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, RT = PG::RT, RS = PG::RS, CW = PG::CW, G = PG::G, NFT = PG::NFT;
@@ -125,12 +152,9 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     uint64_t *acc_free = acc_ready + 1;
     unsigned *heads_done = reinterpret_cast<unsigned *>(acc_free + 1);   // FFT warps that have published their head rows, all tiles so far
 
-    const BlockGeom &g = a.g;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n_tiles = (g.n_streams + T - 1) / T;
-    const int last = g.first_stream + g.n_streams - 1;
-    const int my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int hs = (g.P - 1 + RS - 1) / RS;              // history stages per speaker (groups of RS partitions)
+    const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    auto my_tile = [&](int lt) { return tile_ctx<T, RS>(a, (int)blockIdx.x + lt * (int)gridDim.x); };
 
     for (int k = tid; k < PG::TW; k += PG::THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     if (tid == 0) {
@@ -146,7 +170,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AW_KP_PRODUCER_REGS));
         // ===== producers: warp w fills the ring slots w, w + PRODUCERS, ... every time the stage sequence comes round to them =====
         if (lane == 0) {
-            const size_t stream_stride = (size_t)g.Se * g.P_cap * halfB;
+            const size_t stream_stride = (size_t)a.Se * a.P_cap * halfB;
             const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
             // L2 priorities: history rows are read once per launch (evict first) — they must not push out the head rows the FFT
             // warps have just written, nor the filter bank every tile re-reads (evict last)
@@ -155,20 +179,22 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             // tile lt, column chunk c, and inside the chunk either history group jj of speaker s or the head row of speaker s
             int lt = 0, c = 0, s = 0, jj = 0, stage = 0;
             unsigned phase = 0;
-            bool hist = hs > 0;
+            TileCtx tc = my_tile(0);
+            bool hist = tc.hs > 0;
             auto advance = [&]() {
                 if (hist) {
-                    if (++jj == hs) { jj = 0; if (++s == g.S) { s = 0; hist = false; } }
-                } else if (++s == g.S) {
-                    s = 0; hist = hs > 0;
-                    if (++c == NC) { c = 0; ++lt; }
+                    if (++jj == tc.hs) { jj = 0; if (++s == tc.S) { s = 0; hist = false; } }
+                } else if (++s == tc.S) {
+                    s = 0;
+                    if (++c == NC) { c = 0; ++lt; if (lt < my_tiles) tc = my_tile(lt); }
+                    hist = tc.hs > 0;
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             };
             for (int i = 0; i < warp; ++i) advance();        // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
             while (lt < my_tiles) {
                 const int p0 = hist ? 1 + jj * RS : 0;
-                const int nrows = hist ? min(RS, g.P - p0) : 1;
+                const int nrows = hist ? min(RS, tc.P - p0) : 1;
                 // head rows of tile lt exist once every FFT warp has published them (a monotonic count: no phase to alias)
                 if (!hist) {
                     const unsigned need = (unsigned)(FFT_WARPS * (lt + 1));
@@ -177,22 +203,21 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(heads_done)) : "memory");
                     } while (seen < need);
                 }
-                const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
-                int slot = g.head + p0;
-                if (slot >= g.P) slot -= g.P;                // modulus is partitionCount (Q4)
-                const int n1 = min(nrows, g.P - slot);       // rows before the ring wraps
+                int slot = tc.head + p0;
+                if (slot >= tc.P) slot -= tc.P;              // modulus is partitionCount (Q4)
+                const int n1 = min(nrows, tc.P - slot);      // rows before the ring wraps
                 mbar_wait(&empty[stage], phase ^ 1u);
                 mbar_expect_tx(&full[stage], (unsigned)(nrows * (T + 2) * C * sizeof(float4)));
                 float4 *dst = ring + (size_t)stage * stage_f4;
 #pragma unroll
                 for (int u = 0; u < T; ++u) {
-                    const float4 *row = fdl4 + (size_t)min(s0 + u, last) * stream_stride + (size_t)s * g.P_cap * halfB + c * C;
+                    const float4 *row = fdl4 + (size_t)min(tc.s0 + u, tc.last) * stream_stride + (size_t)s * a.P_cap * halfB + c * C;
                     const uint64_t pol = hist ? pol_stream : pol_keep;
                     bulk_g2s_hint(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage], pol);
                     if (RS > 1 && n1 < nrows)
                         bulk_g2s_hint(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage], pol);
                 }
-                const float4 *frow = a.bank + ((size_t)s * g.P + p0) * M;
+                const float4 *frow = tc.bank + ((size_t)s * tc.P + p0) * M;
                 if (NC == 1) {                               // whole rows: both planes of RS consecutive partitions are contiguous
                     bulk_g2s_hint(dst + T * RS * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage], pol_keep);
                 } else {
@@ -211,14 +236,15 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         const int r = C < 128 ? w / C : 0, jp = C < 128 ? w - r * C : w;
         const int contributor = set * R + r;                 // partial sums are reduced in this order
         // set q drains the ring slots of parity q, i.e. the stages k = q, q + 2, ... of the CTA's stage sequence (STAGES is even)
-        const int head0 = g.S * hs, spc = head0 + g.S;       // first head stage of / stages per column chunk
         int stage = set;                                     // ring slot of my next stage
         unsigned phase = 0;
         int m = set;                                         // my next stage, relative to the current chunk
-        int jj = hs > 0 ? set % hs : 0;                      // its history group (RS > 1 only)
         constexpr int SETS = PG::MAC_SETS;
         for (int lt = 0; lt < my_tiles; ++lt) {
+            const TileCtx tc = my_tile(lt);
+            const int hs = tc.hs, head0 = tc.S * hs, spc = head0 + tc.S;   // first head stage of / stages per column chunk
             for (int c = 0; c < NC; ++c) {
+                int jj = hs > 0 ? m % hs : 0;                // history group of my next stage (RS > 1 only)
                 float4 aL[CW][T], aR[CW][T];
 #pragma unroll
                 for (int v = 0; v < CW; ++v)
@@ -226,7 +252,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     for (int u = 0; u < T; ++u) { aL[v][u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[v][u] = aL[v][u]; }
                 for (; m < spc; m += SETS) {
                     int nrows = 1;                           // head stages carry one row
-                    if (RS > 1 && m < head0) nrows = min(RS, g.P - 1 - jj * RS);
+                    if (RS > 1 && m < head0) nrows = min(RS, tc.P - 1 - jj * RS);
                     mbar_wait(&full[stage], phase);
                     const float4 *src = ring + stage * stage_f4;
 #pragma unroll
@@ -255,7 +281,6 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     if (RS > 1 && hs > 0) { jj += SETS; while (jj >= hs) jj -= hs; }
                 }
                 m -= spc;                                    // position in the next chunk
-                if (RS > 1) jj = hs > 0 ? m % hs : 0;
                 // the FFT warps must be done with the previous tile's accumulators before they are overwritten
                 if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
                 if constexpr (R == 1 && SETS == 1) {
@@ -352,14 +377,14 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         float *my_part = part + (size_t)f * G;
 
         auto forward_tile = [&](int lt) {
-            const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
-            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
-            const int nfft = T * g.S;
+            const TileCtx tc = my_tile(lt);
+            const int s0 = tc.s0, nvalid = tc.nvalid;
+            const int nfft = T * tc.S;
             if (!(a.debug & 1)) {
                 auto fetch = [&](int base, float2 (&v)[F::E], bool &active, int &stream, int &s) {
                     const int idx = base + f;
-                    const int ls = idx / g.S;
-                    s = idx - ls * g.S;
+                    const int ls = idx / tc.S;
+                    s = idx - ls * tc.S;
                     active = idx < nfft && ls < nvalid;
                     stream = s0 + (active ? ls : 0);
                     const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
@@ -374,12 +399,12 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 auto transform = [&](float2 (&v)[F::E], bool active, int stream, int sp) {
                     if (a.debug & 8) {                   // timing experiment: the forward transform's memory traffic without its arithmetic
                         if (active) {
-                            float2 *dst = a.fdl + (((size_t)stream * g.Se + sp) * g.P_cap + g.head) * M;
+                            float2 *dst = a.fdl + (((size_t)stream * a.Se + sp) * a.P_cap + tc.head) * M;
 #pragma unroll
                             for (int e = 0; e < F::E; ++e) {
                                 const int i = F::template load_index<0>(t, e);
                                 dst[i] = v[e];
-                                if (a.overlap_save && i >= M / 2) *reinterpret_cast<float2 *>(a.overlap_save + ((size_t)stream * g.Se + sp) * M + 2 * (i - M / 2)) = v[e];
+                                if (a.overlap_save && i >= M / 2) *reinterpret_cast<float2 *>(a.overlap_save + ((size_t)stream * a.Se + sp) * M + 2 * (i - M / 2)) = v[e];
                             }
                         }
                         return;
@@ -387,14 +412,14 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     if (a.debug & (4 | 16)) active = false;   // timing experiments: 4 = arithmetic without traffic, 16 = loads but no stores,
                                                                 // 32 = stores but no loads
                     if (active && a.overlap_save) {   // inputOverlapBuffer <- current block (:243); this thread read the same addresses as `prev`
-                        float *ov = a.overlap_save + ((size_t)stream * g.Se + sp) * M;
+                        float *ov = a.overlap_save + ((size_t)stream * a.Se + sp) * M;
 #pragma unroll
                         for (int e = 0; e < F::E; ++e) {
                             const int i = F::template load_index<0>(t, e);
                             if (i >= M / 2) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v[e];
                         }
                     }
-                    const size_t row = ((size_t)stream * g.Se + sp) * g.P_cap + g.head;
+                    const size_t row = ((size_t)stream * a.Se + sp) * a.P_cap + tc.head;
                     float2 *dst = a.fdl + row * M;
                     float *dst_ny = a.fdl_ny + row;
                     forward_frame_regs<LOG2M, true>(fftbuf + (size_t)f * PS, tw, t, active, v,
@@ -442,8 +467,10 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         }
 
         auto inverse_tile = [&](int lt) {
-            const int s0 = g.first_stream + ((int)blockIdx.x + lt * (int)gridDim.x) * T;
-            const int nvalid = min(T, g.first_stream + g.n_streams - s0);
+            const TileCtx tc = my_tile(lt);
+            const int s0 = tc.s0, nvalid = tc.nvalid;
+            BlockGeom g;                                         // the Nyquist sum's view of this tile's segment
+            g.S = tc.S; g.Se = a.Se; g.P = tc.P; g.P_cap = a.P_cap; g.head = tc.head;
             for (int base = 0; base < 2 * T; base += NFT) {
                 if (base + warp_first_f >= 2 * T) continue;          // warp-uniform: no transform of this warp has work
                 const int idx = base + f;
@@ -452,7 +479,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 const int stream = s0 + (active ? ls : 0);
                 // idle transforms of a working warp run on their (free) forward buffer so the warp stays converged
                 float2 *buf = idx < 2 * T ? accbuf + (size_t)idx * PS : fftbuf + (size_t)f * PS;
-                const float ny = nyquist_sum<G>(g, a.fdl_ny, a.bank_ny, stream, ear, active, t, my_part, gb);
+                const float ny = nyquist_sum<G>(g, a.fdl_ny, tc.bank_ny, stream, ear, active, t, my_part, gb);
                 if (gw == 0) {
                     float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
                     inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
@@ -544,19 +571,29 @@ int persistent_tiles(int log2m)
     return 0;
 }
 
-cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl, float *fdl_ny,
-                              const float4 *bank, const float *bank_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
+cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_cap, int log2m, StridedIn cur, StridedIn prev,
+                              float *overlap_save, float2 *fdl, float *fdl_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
                               int debug, const EqFuse &eq, cudaStream_t st)
 {
-    if (g.n_streams <= 0) return cudaSuccess;
-    if (!(persistent_tiles(g.log2m) & tile)) return cudaErrorInvalidValue;
-    if (eq.n_filters != 0 && (!persistent_can_fuse_eq(g.log2m, tile, eq.n_filters) || out.ring_cap > 0)) return cudaErrorInvalidValue;
-    PersistArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, bank, bank_ny, out, tw, debug, eq};
-    const int tiles = (g.n_streams + tile - 1) / tile;
+    if (n_segs <= 0) return cudaSuccess;
+    if (n_segs > kKpMaxSegments || !(persistent_tiles(log2m) & tile)) return cudaErrorInvalidValue;
+    if (eq.n_filters != 0 && (n_segs != 1 || !persistent_can_fuse_eq(log2m, tile, eq.n_filters) || out.ring_cap > 0)) return cudaErrorInvalidValue;
+    PersistArgs a;
+    memset(&a, 0, sizeof(a));
+    int tiles = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        a.seg[i] = segs[i];
+        a.seg[i].tile0 = tiles;
+        tiles += (segs[i].n_streams + tile - 1) / tile;
+    }
+    if (tiles <= 0) return cudaSuccess;
+    a.n_segs = n_segs; a.n_tiles = tiles; a.Se = Se; a.P_cap = P_cap;
+    a.cur = cur; a.prev = prev; a.overlap_save = overlap_save; a.fdl = fdl; a.fdl_ny = fdl_ny; a.out = out; a.tw = tw;
+    a.debug = debug; a.eq = eq;
     const int ctas = tiles < max_ctas ? tiles : max_ctas;
 #define AW_KP(L, TT) return launch_persistent_lt<L, TT>(a, ctas, st)
     if (tile == 4) {
-        switch (g.log2m) {
+        switch (log2m) {
         case 6: AW_KP(6, 4);
         case 7: AW_KP(7, 4);
         case 8: AW_KP(8, 4);
@@ -564,7 +601,7 @@ cudaError_t launch_persistent(const BlockGeom &g, StridedIn cur, StridedIn prev,
         default: return cudaErrorInvalidValue;
         }
     }
-    switch (g.log2m) {
+    switch (log2m) {
     case 6: AW_KP(6, 2);
     case 7: AW_KP(7, 2);
     case 8: AW_KP(8, 2);

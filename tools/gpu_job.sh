@@ -1,3 +1,3 @@
 #!/bin/bash
-PYTEST_TIMEOUT=1800 PYTEST_ARGS="--timeout 900" bash tools/gpu_check.sh
-timeout 900 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize.py 2>&1 | grep -E "ERROR SUMMARY|1024|2048"
+bash tools/bench_all.sh F3
+timeout 600 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "many_profile or c2_full" --timeout 600 2>&1 | tail -2
