@@ -75,8 +75,10 @@ int get_plan(int device, int log2n, const float2 **out)
         tw[k] = make_float2((float)std::cos(a), (float)std::sin(a));
     }
     float2 *d = nullptr;
-    AW_CUDA(cudaMalloc(&d, sizeof(float2) * half));
+    AW_CUDA(cudaMalloc(&d, sizeof(float2) * (half + plan_pt_entries(log2n - 1))));
     cudaError_t e = cudaMemcpy(d, tw.data(), sizeof(float2) * half, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_build_pt(log2n - 1, d, d + half, 0);   // per-pass tables derived from the same values
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { cudaFree(d); return set_error(AW_ERR_CUDA, std::string("plan upload: ") + cudaGetErrorString(e)); }
     e = configure_kernels(log2n - 1);
     if (e != cudaSuccess) { cudaFree(d); return set_error(AW_ERR_CUDA, std::string("configure_kernels: ") + cudaGetErrorString(e)); }

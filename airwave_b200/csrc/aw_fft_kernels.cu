@@ -23,8 +23,11 @@ struct Geo {
     static constexpr int SA_THREADS = G > 128 ? G : 128;      // stand-alone K1/K2/K4
     static constexpr int SA_NF = SA_THREADS / G;
     static constexpr int PS = PaddedSize<LOG2M>::value;
-    static constexpr int TW = pt_total_entries(LOG2M) > M ? pt_total_entries(LOG2M) : M;   // room for either twiddle layout
-    static constexpr size_t sa_smem = (size_t)(TW + SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
+    // K1 keeps the half-circle twiddle table in shared memory; K2/K4 read the per-pass tables (PT layout, conflict-free and
+    // coalesced: k contiguous) straight from the plan in global memory — L1 serves them — so that a CTA needs nothing but its
+    // transform buffers and 3x as many CTAs fit on an SM at B = 4096
+    static constexpr size_t k1_smem = (size_t)(M + SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
+    static constexpr size_t sa_smem = (size_t)(SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -45,12 +48,9 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_input_rfft(const Inp
     using Gm = Geo<LOG2M>;
     constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufs = tw + Gm::TW;
+    float2 *bufs = reinterpret_cast<float2 *>(smem_raw);
+    const float2 *tw = a.tw + M;          // the plan's per-pass twiddle tables (global memory, read through L1)
     const int tid = threadIdx.x, f = tid / G, t = tid % G;
-    // per-pass twiddle tables (conflict-free reads), built once per CTA and amortised over the CTA's share of the frames
-    for (int k = tid; k < pt_total_entries(LOG2M); k += Gm::SA_THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
-    __syncthreads();
     const int jobs = a.g.n_streams * a.g.S;
     for (int base = blockIdx.x * NF; base < jobs; base += gridDim.x * NF) {   // uniform trip count: barriers inside
         const int job = base + f;
@@ -144,18 +144,17 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const Irff
     using Gm = Geo<LOG2M>;
     constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *tw = reinterpret_cast<float2 *>(smem_raw);
-    float2 *bufs = tw + Gm::TW;
+    float2 *bufs = reinterpret_cast<float2 *>(smem_raw);
+    const float2 *tw = a.tw + M;          // the plan's per-pass twiddle tables (global memory, read through L1)
     float *part = reinterpret_cast<float *>(bufs + (size_t)NF * Gm::PS);
     const int tid = threadIdx.x, f = tid / G, t = tid % G;
-    for (int k = tid; k < pt_total_entries(LOG2M); k += Gm::SA_THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     float2 *buf = bufs + (size_t)f * Gm::PS;
     const int jobs = a.g.n_streams * 2;   // (local stream, ear)
     for (int base = blockIdx.x * NF; base < jobs; base += gridDim.x * NF) {   // uniform trip count: barriers inside
         const int job = base + f;
         const bool active = job < jobs;
         const int stream = a.g.first_stream + (active ? job >> 1 : 0), ear = job & 1;
-        __syncthreads();                  // the previous round is done with buf (and the table is complete)
+        __syncthreads();                  // the previous round is done with buf
         if (active) {
             const float2 *src = a.acc + ((size_t)stream * 2 + ear) * M;
             for (int k = t; k < M; k += G) buf[pad16(k)] = src[k];
@@ -449,7 +448,37 @@ cudaError_t launch_bank_build(const float *ir, int S, int taps, int B, int log2m
 {
     const int jobs = S * 2 * P;
     BankArgs a{ir, S, taps, B, P, bank, bank_ny, tw};
-#define CALL(L) k_bank_build<L><<<(jobs + Geo<L>::SA_NF - 1) / Geo<L>::SA_NF, Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+#define CALL(L) k_bank_build<L><<<(jobs + Geo<L>::SA_NF - 1) / Geo<L>::SA_NF, Geo<L>::SA_THREADS, Geo<L>::k1_smem, st>>>(a)
+    AW_LOG2M_SWITCH(log2m, CALL)
+#undef CALL
+    return cudaGetLastError();
+}
+
+// ---- plan: per-pass twiddle tables appended to the half-circle table ---------------------------------
+template <int LOG2M>
+__global__ void k_build_pt(const float2 *hc, float2 *pt)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < pt_total_entries(LOG2M); i += gridDim.x * blockDim.x)
+        pt[i] = RegFft<LOG2M>::pt_entry(hc, i);
+}
+
+int plan_pt_entries(int log2m)
+{
+    int n = 0;
+#define CALL(L) n = pt_total_entries(L)
+    switch (log2m) {
+    case 2: CALL(2); break;   case 3: CALL(3); break;   case 4: CALL(4); break;   case 5: CALL(5); break;
+    case 6: CALL(6); break;   case 7: CALL(7); break;   case 8: CALL(8); break;   case 9: CALL(9); break;
+    case 10: CALL(10); break; case 11: CALL(11); break; case 12: CALL(12); break; case 13: CALL(13); break;
+    default: break;
+    }
+#undef CALL
+    return n;
+}
+
+cudaError_t launch_build_pt(int log2m, const float2 *hc, float2 *pt, cudaStream_t st)
+{
+#define CALL(L) k_build_pt<L><<<8, 256, 0, st>>>(hc, pt)
     AW_LOG2M_SWITCH(log2m, CALL)
 #undef CALL
     return cudaGetLastError();
@@ -557,7 +586,9 @@ cudaError_t configure_kernels(int log2m)
         if (Geo<L>::sa_smem > 48 * 1024) {                                                                                   \
             if ((e = cudaFuncSetAttribute(k_input_rfft<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e; \
             if ((e = cudaFuncSetAttribute(k_irfft_out<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e;  \
-            if ((e = cudaFuncSetAttribute(k_bank_build<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e; \
+        }                                                                                                                    \
+        if (Geo<L>::k1_smem > 48 * 1024) {                                                                                   \
+            if ((e = cudaFuncSetAttribute(k_bank_build<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::k1_smem)) != cudaSuccess) return e; \
         }                                                                                                                    \
     } while (0)
     AW_LOG2M_SWITCH(log2m, CALL)

@@ -103,6 +103,10 @@ cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_c
                               float *overlap_save, float2 *fdl, float *fdl_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
                               int debug, const EqFuse &eq, cudaStream_t st);
 
+// Plan layout in global memory: M half-circle twiddles exp(-2*pi*i*k/(2M)) followed by plan_pt_entries(log2m) per-pass
+// twiddles (RegFft::pt_entry layout), M = 2^log2m complex points.
+int plan_pt_entries(int log2m);
+cudaError_t launch_build_pt(int log2m, const float2 *hc, float2 *pt, cudaStream_t st);
 size_t fft_smem_bytes(int log2m);
 cudaError_t configure_kernels(int log2m);   // opt in to > 48 KB dynamic shared memory for that transform size
 

@@ -1,3 +1,4 @@
 #!/bin/bash
-bash tools/bench_all.sh F3
-timeout 600 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "many_profile or c2_full" --timeout 600 2>&1 | tail -2
+PYTEST_TIMEOUT=1800 PYTEST_ARGS="--timeout 900" bash tools/gpu_check.sh
+bash tools/bench_all.sh C5-4096
+BENCH_ENV="AW_FUSED_TILE=0" bash tools/bench_all.sh C5-2048 C5-1024 C2
