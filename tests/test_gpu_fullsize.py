@@ -313,3 +313,43 @@ def test_bank_with_fewer_speakers_than_the_engine_has_channels(aw, hrtf_path):
     h = oracle.hrir_matrix(oracle.load_wav(hrtf_path("RoomSH1.0")), FS, oracle.InputLayout.surround51)
     ref = oracle.direct_conv_f64(x[3, :6], h)
     assert np.abs(yw[3] - ref).max() <= MAX_ABS and snr_db(ref, yw[3]) >= SNR_DB
+
+
+def test_long_run_does_not_drift(aw, hrtf_path):
+    """600 blocks (3.2 s of audio, the FDL ring wraps 35 times, ragged callback sizes in the middle): the output stays within the
+    bound of float64 convolution from the first sample to the last."""
+    from scipy.signal import fftconvolve
+    lay = aw.InputLayout.surround71()
+    wav_o = oracle.load_wav(hrtf_path("RoomSH1.0"))
+    h = oracle.hrir_matrix(wav_o, FS, oracle.InputLayout.surround71)
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), FS, lay, 256)
+    n, frames = 6, 600 * 256
+    x = oracle.synth_block(SEED, [2, 9, 4, 7, 1, 8], 8, 0, frames)
+    eng = aw.BinauralEngine(n, 8, 256, FS, max_frames_per_call=4096)
+    eng.set_bank(bank)
+    sizes, pos, outs = [], 0, []
+    rng = np.random.default_rng(5)
+    while pos < frames:
+        size = 4096 if (pos // 4096) % 7 != 3 else int(rng.integers(1, 4096))   # mostly aligned, now and then ragged
+        size = min(size, frames - pos)
+        outs.append(eng.process(np.ascontiguousarray(x[:, :, pos:pos + size])))
+        pos += size
+    y = np.concatenate(outs, axis=2)
+    eng.close()
+    # ragged calls switch the engine to the adapter (pending/FIFO) path for good: from the first ragged call on the output is the
+    # convolution delayed by a whole number of frames d < 256 (RealtimeAudioProcessor.swift:88-116); find d from stream 0
+    ref0 = np.zeros((2, frames))
+    for s in range(8):
+        ref0[0] += fftconvolve(x[0, s].astype(np.float64), h[s, 0].astype(np.float64))[:frames]
+        ref0[1] += fftconvolve(x[0, s].astype(np.float64), h[s, 1].astype(np.float64))[:frames]
+    tail = slice(frames - 20000, frames)
+    best = min(range(0, 257), key=lambda d: np.abs(y[0, 0, tail] - np.roll(ref0[0], d)[tail]).max())
+    for i in range(n):
+        ref = np.zeros((2, frames))
+        for s in range(8):
+            ref[0] += fftconvolve(x[i, s].astype(np.float64), h[s, 0].astype(np.float64))[:frames]
+            ref[1] += fftconvolve(x[i, s].astype(np.float64), h[s, 1].astype(np.float64))[:frames]
+        got, want = y[i][:, tail], np.roll(ref, best, axis=1)[:, tail]
+        assert np.abs(got - want).max() <= MAX_ABS, (i, best)
+        assert snr_db(want, got) >= SNR_DB
+        assert np.abs(y[i][:, :4096] - ref[:, :4096]).max() <= MAX_ABS       # before the first ragged call: no delay at all

@@ -1,4 +1,2 @@
 #!/bin/bash
-PYTEST_TIMEOUT=1800 PYTEST_ARGS="--timeout 900" bash tools/gpu_check.sh
-bash tools/bench_all.sh C5-4096
-BENCH_ENV="AW_FUSED_TILE=0" bash tools/bench_all.sh C5-2048 C5-1024 C2
+timeout 900 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "long_run" --timeout 600 2>&1 | tail -15
