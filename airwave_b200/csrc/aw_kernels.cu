@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(64) k_eq(const EqLaunch l, double *__restrict_
 // floor(32/gw) channels.  Same operations in the same order per biquad as ParametricEqualizerState.process (:65-90): bit-exact.
 __global__ void __launch_bounds__(128) k_eq_systolic(const EqLaunch l, int gw, double *__restrict__ zstate, StridedOut io)
 {
-    __shared__ float stage_s[4][1024];                      // per warp: `groups` channels x `chunk` frames, staged coalesced
+    constexpr int kPerWarp = 1024;                          // doubles of staging per warp (>= 32 frames for each of up to 32 channels)
+    __shared__ double stage_s[4][kPerWarp];                 // per warp: `groups` channels x `chunk` frames, staged coalesced
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int groups = 32 / gw;
     const int g = lane / gw, f = lane - g * gw;
@@ -274,36 +275,43 @@ __global__ void __launch_bounds__(128) k_eq_systolic(const EqLaunch l, int gw, d
         b0 = prog->coef[f][0]; b1 = prog->coef[f][1]; b2 = prog->coef[f][2]; a1 = prog->coef[f][3]; a2 = prog->coef[f][4];
         z1 = zp[0]; z2 = zp[1];
     }
-    const int chunk = (1024 / groups) & ~31;                // frames per channel staged at a time (a multiple of 32)
-    float *mine = stage_s[wid] + (g < groups ? g : 0) * chunk;
+    const int chunk = (kPerWarp / groups) & ~31;            // frames per channel staged at a time (a multiple of 32)
+    double *mine = stage_s[wid] + (g < groups ? g : 0) * chunk;
+    const bool first = f == 0, last_f = f == gw - 1;
     for (int c0 = 0; c0 < l.seg_len; c0 += chunk) {
         const int cl = min(chunk, l.seg_len - c0);
-        for (int q = 0; q < groups && ch0 + q < total; ++q) {   // coalesced: the warp copies one channel's frames at a time
+        // coalesced load, one channel at a time; the float -> double conversion and the preamp (:66) happen here, in parallel,
+        // instead of on the serial path below
+        for (int q = 0; q < groups && ch0 + q < total; ++q) {
             const long long cq = ch0 + q;
             const float *src = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + l.seg_start + c0;
-            for (int i = lane; i < cl; i += 32) stage_s[wid][q * chunk + i] = src[i];
+            for (int i = lane; i < cl; i += 32) stage_s[wid][q * chunk + i] = __dmul_rn((double)src[i], pre);
         }
         __syncwarp();
         double y = 0.0;                                     // my output of the previous step
-        for (int t = 0; t < cl + gw - 1; ++t) {
+        auto step = [&](int t, bool active) {
             const double up = __shfl_up_sync(0xffffffffu, y, 1);
-            const int i = t - f;                            // the sample this lane filters now
-            if (live && i >= 0 && i < cl) {
-                const double x = f == 0 ? __dmul_rn((double)mine[i], pre) : up;   // preamp first (:66)
+            if (active) {
+                const int i = t - f;                        // the sample this lane filters now
+                const double x = first ? mine[i] : up;
                 // no FMA contraction: the reference (and the oracle) round every product and sum (:73-75)
                 y = __dadd_rn(__dmul_rn(b0, x), z1);
                 const double n1 = __dadd_rn(__dsub_rn(__dmul_rn(b1, x), __dmul_rn(a1, y)), z2);
                 const double n2 = __dsub_rn(__dmul_rn(b2, x), __dmul_rn(a2, y));
                 z1 = flush_subnormal(n1);
                 z2 = flush_subnormal(n2);
-                if (f == gw - 1) mine[i] = (float)y;        // :88-89 (in place: sample i was consumed gw-1 steps ago)
+                if (last_f) mine[i] = y;                    // in place: sample i was consumed gw-1 steps ago
             }
-        }
+        };
+        const int ramp = min(gw - 1, cl);
+        for (int t = 0; t < ramp; ++t) step(t, live && f <= t);                    // pipeline fills
+        for (int t = ramp; t < cl; ++t) step(t, live);                             // every lane has a sample
+        for (int t = cl; t < cl + gw - 1; ++t) step(t, live && t - f >= 0 && t - f < cl);   // pipeline drains
         __syncwarp();
-        for (int q = 0; q < groups && ch0 + q < total; ++q) {
+        for (int q = 0; q < groups && ch0 + q < total; ++q) {                       // :88-89, coalesced
             const long long cq = ch0 + q;
             float *dst = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + l.seg_start + c0;
-            for (int i = lane; i < cl; i += 32) dst[i] = stage_s[wid][q * chunk + i];
+            for (int i = lane; i < cl; i += 32) dst[i] = (float)stage_s[wid][q * chunk + i];
         }
         __syncwarp();
     }

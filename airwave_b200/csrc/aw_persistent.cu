@@ -1,31 +1,31 @@
 // aw_persistent.cu — KP: the persistent warp-specialised block kernel (64 <= B <= 2048), the default hot path.
 //
-// One CTA per SM walks over tiles of T streams (T = 4 or 2).  For every tile it does what 2*S ConvolutionEngine.process
-// calls plus the RealtimeAudioProcessor mix do for T streams (ConvolutionEngine.swift:232-367, RealtimeAudioProcessor.swift:
-// 146-163): forward real FFT of the T*S overlap-save frames, frequency-domain delay-line multiply-accumulate over all
-// (speaker, partition) pairs for both ears, inverse real FFT with the overlap-save discard.
+// One CTA per SM walks over tiles of T streams (T = 4 up to B = 512, 2 above).  For every tile it does what 2*S
+// ConvolutionEngine.process calls plus the RealtimeAudioProcessor mix do for T streams (ConvolutionEngine.swift:232-367,
+// RealtimeAudioProcessor.swift:146-163): forward real FFT of the T*S overlap-save frames, frequency-domain delay-line
+// multiply-accumulate over all (speaker, partition) pairs for both ears, inverse real FFT with the overlap-save discard.
+// One launch serves every stream range ("segment": streams bound to the same bank) of the engine; a tile looks its segment up.
 //
-//   4 producer warps    one elected lane each; producer w issues the stages k = w, w+4, ... of this CTA's stage sequence:
-//                       FDL rows and the matching filter rows go into a deep shared-memory ring with TMA-class bulk copies
-//                       (cp.async.bulk ... mbarrier::complete_tx).  (UBLKCP takes uniform operands, so lane-parallel issue
-//                       would be serialised by the compiler; independent warps really do issue in parallel.)  A stage holds
-//                       R consecutive partitions of one speaker x C bin pairs for the T streams: C = min(B/2, 128) and
-//                       R = 128/C, i.e. always 128 bin-pair lanes of work per stream group whatever the block size; the
-//                       R FDL rows of a stream are consecutive ring slots, so they travel as one copy (two at the wrap).
-//                       Rows wider than 128 bin pairs are walked in column chunks (accumulators stay in registers for the
-//                       whole chunk).
-//   8 MAC warps         (4 from B = 1024) two sets of 128 threads that take alternate stages; a thread owns one bin pair (two complex bins, one
-//                       float4 of FDL) of one row of the stage for ALL T streams and both ears, so a filter value is read
-//                       from shared memory once per T streams (shared-memory bandwidth is the resource next to HBM here).
-//                       full/empty mbarriers per stage.  The partial sums of the sets (and of the R rows) are reduced
+//   producer warps      (4; 3 at B >= 512 with T = 4) one elected lane each; producer w fills the ring slots w, w+4, ...: FDL rows
+//                       and the matching filter rows go into a shared-memory ring with TMA-class bulk copies (cp.async.bulk ...
+//                       mbarrier::complete_tx).  UBLKCP takes uniform operands (lane-parallel issue would be serialised by the
+//                       compiler), costs its issuing thread ~155 cycles and the copy engine ~40 cycles whatever its size
+//                       (tools/tmabw.cu) — so a stage is few, large copies: RS consecutive partitions of one speaker x C bin
+//                       pairs for the T streams, 4 KB of FDL per stream and copy (consecutive partitions are consecutive ring
+//                       slots: one copy, two at the wrap), the filter rows in one 8 KB copy.  Rows wider than C bin pairs are
+//                       walked in column chunks (accumulators stay in registers for the whole chunk).
+//   MAC warps           (8; 4 from B = 1024) sets of 128 threads that take alternate stages; a thread owns one bin pair (two at
+//                       B >= 512) of RT rows of the stage for ALL T streams and both ears, so a filter value is read from shared
+//                       memory once per T streams (shared-memory bandwidth is the resource next to HBM here).  full/empty
+//                       mbarriers per ring slot.  The partial sums of the sets (and of the R rows side by side) are reduced
 //                       through shared memory in a fixed order (deterministic).
-//   4, 8 or 12 FFT warps  run the forward transforms ONE TILE AHEAD of the MAC warps (nothing but the head slot of the FDL
-//                       depends on them), and the inverse transforms of the tile the MAC warps just finished
+//   FFT warps           (4, 8 or 12) run the forward transforms ONE TILE AHEAD of the MAC warps (nothing but the head slot of
+//                       the FDL depends on them), and the inverse transforms of the tile the MAC warps just finished
 //                       (accumulators handed over through shared memory, acc_ready/acc_free mbarriers).
 //
 // The head partition (p = 0) is streamed like any other row: the FFT warps publish it with a generic->async proxy fence
 // + a monotonic shared-memory count (release/acquire), which a producer checks before it issues a head row of a tile.
-// Stage order inside a tile (and column chunk): for every speaker its history partitions p = 1..P-1 in groups of R, then
+// Stage order inside a tile (and column chunk): for every speaker its history partitions p = 1..P-1 in groups of RS, then
 // the S head rows — the same for every tile size and stream count, so a stream's output does not depend on how many
 // streams the engine renders or on which GPU it lives.
 #include <string.h>
@@ -59,15 +59,6 @@ template <int LOG2M, int T> struct PGeo {
     // threads hold 2 bin pairs x 4 streams x 2 ears of accumulators); at B = 512 the 6 ring slots divide evenly among them.
     static constexpr int PRODUCERS = LOG2M >= 9 && T == 4 ? 3 : 4;
     static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
-    // Experiment switch (off): hand registers from the producer warpgroup to the MAC warpgroups with setmaxnreg.  It produced
-    // sporadic whole-tile corruption at B = 512, T = 4 that the register indices in the SASS do not explain; see DESIGN.md.
-#ifndef AW_KP_REBALANCE
-#define AW_KP_REBALANCE 0
-#endif
-#ifndef AW_KP_PRODUCER_REGS
-#define AW_KP_PRODUCER_REGS 40
-#endif
-    static constexpr bool REBALANCE = AW_KP_REBALANCE && PRODUCERS == 4 && THREADS > 512 && CW > 1;
     static constexpr int PS = PaddedSize<LOG2M>::value;
     static constexpr int stage_f4 = RS * (T + 2) * C;        // FDL [T][RS][C] + filter [RS][2 planes][C] float4
     static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
@@ -83,10 +74,9 @@ template <int LOG2M, int T> struct PGeo {
     // two sets alternating across the wrap.
     static constexpr int STAGES = (max_stages > 32 ? 32 : max_stages) / 2 * 2;
     static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
-#ifndef AW_KP_PREFETCH_MAX
-#define AW_KP_PREFETCH_MAX 8
-#endif
-    static constexpr bool PREFETCH = LOG2M <= AW_KP_PREFETCH_MAX;   // next round's operands fetched while this round transforms
+    // next round's operands fetched while this round transforms — only where the registers exist (with 96-104 registers per
+    // thread at B >= 512 the spills cost more than the exposed latency: measured)
+    static constexpr bool PREFETCH = LOG2M <= 8;
     static_assert(STAGES >= PRODUCERS && STAGES % MAC_SETS == 0 && (MAC_SETS == 2 || R == 1), "ring geometry");
     static_assert(NC == 1 || RS == 1, "column chunks carry one row per stage");
 };
@@ -167,7 +157,6 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     __syncthreads();
 
     if (warp < PRODUCERS) {
-        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(AW_KP_PRODUCER_REGS));
         // ===== producers: warp w fills the ring slots w, w + PRODUCERS, ... every time the stage sequence comes round to them =====
         if (lane == 0) {
             const size_t stream_stride = (size_t)a.Se * a.P_cap * halfB;
@@ -229,7 +218,6 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             }
         }
     } else if (warp < PRODUCERS + MAC_WARPS) {
-        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         // ===== MAC warps: set q consumes the stages k = q (mod 2); a thread owns one bin pair of one row, all T streams =====
         const int mt = tid - 32 * PRODUCERS;
         const int set = mt >> 7, w = mt & 127;
@@ -368,7 +356,6 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         }
     } else {
         // ===== FFT warps =====
-        if constexpr (PG::REBALANCE) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
         using F = RegFft<LOG2M>;
         const int ft = tid - 32 * PRODUCERS - PG::MAC_THREADS;
         const int f = ft / G, t = ft - f * G;

@@ -1,2 +1,4 @@
 #!/bin/bash
-timeout 900 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "long_run" --timeout 600 2>&1 | tail -15
+timeout 240 python -m pytest tests/test_gpu_eq.py -m gpu -x -q --timeout 60 2>&1 | tail -3
+timeout 240 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "c4 or fused_eq" --timeout 120 2>&1 | tail -3
+timeout 200 bash tools/bench_all.sh C4
