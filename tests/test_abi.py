@@ -200,3 +200,11 @@ def test_swift_shim_and_module_map_are_shipped():
         assert name in swift
     used = set(__import__("re").findall(r"\b(aw_[a-z0-9_]+)\(", swift)) - {"aw_engine_config"}   # struct initialiser, not a call
     assert used and used <= set(aw.declared_symbols())
+    # the app-target file: the two effects AudioEffectGraph composes (AudioEffectGraph.swift:47-54), every C call declared in the header
+    effects = open(os.path.join(ROOT, "airwave_b200", "swift", "AirwaveCUDAEffects.swift")).read()
+    for name in ("class CUDASpatialEffect: AudioSpatialEffect", "class CUDAEqualizerEffect: AudioEqualizerEffect",
+                 "func prepare(definition: EqualizerDefinition?, sampleRate: Double) throws",
+                 "func setTarget(definition: EqualizerDefinition?) throws", "var isReady"):
+        assert name in effects, name
+    used = set(__import__("re").findall(r"\b(aw_[a-z0-9_]+)\(", effects)) - {"aw_engine_config", "aw_eq_filter"}
+    assert used and used <= set(aw.declared_symbols()), used - set(aw.declared_symbols())
