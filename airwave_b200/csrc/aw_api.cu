@@ -154,6 +154,7 @@ struct aw_engine {
     static constexpr int kSideStreams = 8;
     cudaStream_t side[kSideStreams] = {};
     cudaEvent_t forkEvent = nullptr, joinEvent[kSideStreams] = {};
+    cudaStream_t eqStream = nullptr;   // where the equalizer of the machine being processed launches (the main stream, or a side stream)
     std::vector<Segment> segments;
     std::vector<EqMachine> machines;
     // EQ state-object pool (host mirror of the programs resident on the device)
@@ -288,7 +289,7 @@ int eq_begin_transition(aw_engine *e, EqMachine &m, int target)   // :354-359
     eq_assign(e, m.transitionTo, target);
     m.transitionFrame = 0;
     // the target state object starts with zero history: clear the voice it will run on
-    AW_LAUNCH(e, launch_eq_reset(e->d_eq_z, m.first, m.count, 1 << (1 - m.activeVoice), e->stream));
+    AW_LAUNCH(e, launch_eq_reset(e->d_eq_z, m.first, m.count, 1 << (1 - m.activeVoice), e->eqStream));
     return AW_OK;
 }
 
@@ -358,7 +359,7 @@ int eq_apply_pending_reset(aw_engine *e, EqMachine &m)   // :341-352
 {
     if (!m.resetRequested) return AW_OK;
     m.resetRequested = false;
-    AW_LAUNCH(e, launch_eq_reset(e->d_eq_z, m.first, m.count, 3, e->stream));
+    AW_LAUNCH(e, launch_eq_reset(e->d_eq_z, m.first, m.count, 3, e->eqStream));
     return AW_OK;
 }
 
@@ -406,7 +407,7 @@ int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
             l.to_voice = 1 - m.activeVoice;
             l.seg_start = offset;
             l.seg_len = frames - offset;
-            AW_LAUNCH(e, launch_eq(l, e->eqFilters[a], e->d_eq_z, io, e->stream));
+            AW_LAUNCH(e, launch_eq(l, e->eqFilters[a], e->d_eq_z, io, e->eqStream));
             return AW_OK;
         }
         const int remaining = e->transitionLength - m.transitionFrame;
@@ -418,7 +419,7 @@ int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
         l.seg_start = offset;
         l.seg_len = segment;
         l.transition_frame = m.transitionFrame;
-        AW_LAUNCH(e, launch_eq(l, std::max(e->eqFilters[m.transitionFrom], e->eqFilters[m.transitionTo]), e->d_eq_z, io, e->stream));
+        AW_LAUNCH(e, launch_eq(l, std::max(e->eqFilters[m.transitionFrom], e->eqFilters[m.transitionTo]), e->d_eq_z, io, e->eqStream));
         m.transitionFrame += segment;
         offset += segment;
         if (m.transitionFrame == e->transitionLength && (rc = eq_finish_transition(e, m)) != AW_OK) return rc;
@@ -591,11 +592,47 @@ int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, 
     // equalizer after spatial (AudioEffectGraph.swift:195-210), in place on the output
     const bool prof = e->profOn && e->profEqUsed + 2 <= e->profEqEvents.size();
     if (prof) cudaEventRecord(e->profEqEvents[e->profEqUsed], e->stream);
+    // several stream ranges with their own equalizers (per-device profiles): their cascades are independent, so they run
+    // concurrently on the side streams and join before the call's output is handed back
+    int active_machines = 0;
+    for (const EqMachine &m : e->machines) active_machines += m.eqActive && m.hasProcessor;
+    const bool fork_eq = fused.n_filters == 0 && active_machines >= 2 && !e->profOn;
+    const int lanes = fork_eq ? std::min(active_machines, (int)aw_engine::kSideStreams) : 0;
+    if (fork_eq) {
+        AW_CUDA(cudaEventRecord(e->forkEvent, e->stream));
+        for (int k = 0; k < lanes; ++k) AW_CUDA(cudaStreamWaitEvent(e->side[k], e->forkEvent, 0));
+    }
+    int ordinal = 0, eq_rc = AW_OK;
+    // ranges in steady state (no crossfade running) share ONE launch of the systolic kernel, whatever their equalizers
+    EqSegment steady[kEqMaxSegments];
+    int n_steady = 0;
     for (EqMachine &m : e->machines) {
         if (fused.n_filters != 0) continue;              // already applied by the block kernel
-        const int rc = eq_process_machine(e, m, out, frames);
-        if (rc != AW_OK) return rc;
+        const int act = m.activeState;
+        const bool is_steady = active_machines >= 2 && m.eqActive && m.hasProcessor && m.transitionFrom < 0 && m.transitionTo < 0 &&
+                               e->eqFilters[act] >= 1 && e->eqFilters[act] <= 32 && n_steady < kEqMaxSegments;
+        if (is_steady) {
+            steady[n_steady++] = EqSegment{m.first, m.count, e->eqFilters[act], m.activeVoice, 0, 0, e->d_eq_prog + act};
+            continue;
+        }
+        if (fork_eq && m.eqActive && m.hasProcessor) e->eqStream = e->side[ordinal++ % lanes];
+        eq_rc = eq_process_machine(e, m, out, frames);
+        e->eqStream = e->stream;
+        if (eq_rc != AW_OK) break;
     }
+    if (eq_rc == AW_OK && n_steady > 0) {
+        const cudaStream_t st = fork_eq ? e->side[ordinal++ % lanes] : e->stream;
+        cudaError_t le = launch_eq_steady(steady, n_steady, 0, frames, e->d_eq_z, out, st);
+        ++e->launches;
+        if (le != cudaSuccess) eq_rc = set_error(AW_ERR_CUDA, std::string("launch_eq_steady: ") + cudaGetErrorString(le));
+    }
+    if (fork_eq) {
+        for (int k = 0; k < lanes; ++k) {
+            AW_CUDA(cudaEventRecord(e->joinEvent[k], e->side[k]));
+            AW_CUDA(cudaStreamWaitEvent(e->stream, e->joinEvent[k], 0));
+        }
+    }
+    if (eq_rc != AW_OK) return eq_rc;
     if (prof) { cudaEventRecord(e->profEqEvents[e->profEqUsed + 1], e->stream); e->profEqUsed += 2; }
     return AW_OK;
 }
@@ -900,6 +937,7 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         AW_TRY(cudaEventCreateWithFlags(&e->joinEvent[k], cudaEventDisableTiming));
     }
     AW_TRY(cudaEventCreateWithFlags(&e->forkEvent, cudaEventDisableTiming));
+    e->eqStream = e->stream;
     const size_t n = e->n, S = e->S, B = e->B;
     AW_TRY(cudaMalloc(&e->d_overlap, n * S * B * sizeof(float)));
     AW_TRY(cudaMalloc(&e->d_pending, n * S * B * sizeof(float)));

@@ -17,6 +17,7 @@
 #include "aw_kernels.h"
 
 #include <stdint.h>
+#include <string.h>
 
 
 namespace aw {
@@ -253,24 +254,35 @@ __global__ void __launch_bounds__(64) k_eq(const EqLaunch l, double *__restrict_
 // step t filters sample t - f, taking its input from lane f-1's output of the previous step (two 32-bit shuffles).  The
 // per-sample critical path is one biquad instead of n_filters, every lane does useful float64 work, and a warp carries
 // floor(32/gw) channels.  Same operations in the same order per biquad as ParametricEqualizerState.process (:65-90): bit-exact.
-__global__ void __launch_bounds__(128) k_eq_systolic(const EqLaunch l, int gw, double *__restrict__ zstate, StridedOut io)
+struct EqSteadyArgs {
+    int n_segs, seg_start, seg_len, total_warps;
+    EqSegment seg[kEqMaxSegments];
+};
+
+__global__ void __launch_bounds__(128) k_eq_systolic(const __grid_constant__ EqSteadyArgs a, double *__restrict__ zstate, StridedOut io)
 {
     constexpr int kPerWarp = 1024;                          // doubles of staging per warp (>= 32 frames for each of up to 32 channels)
     __shared__ double stage_s[4][kPerWarp];                 // per warp: `groups` channels x `chunk` frames, staged coalesced
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int gwarp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (gwarp >= a.total_warps) return;
+    int si = 0;                                             // the stream range (equalizer) this warp serves
+    while (si + 1 < a.n_segs && gwarp >= a.seg[si + 1].warp0) ++si;
+    const EqSegment &l = a.seg[si];
+    const int gw = l.n_filters;
     const int groups = 32 / gw;
     const int g = lane / gw, f = lane - g * gw;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long ch0 = warp * groups;                    // first channel (= stream*2 + ear within the launch) of this warp
+    const long long warp = gwarp - l.warp0;
+    const long long ch0 = warp * groups;                    // first channel (= stream*2 + ear within the range) of this warp
     const long long total = (long long)l.n_streams * 2;
     if (ch0 >= total) return;                               // whole warp idle
     const long long ch = ch0 + g;
     const bool live = g < groups && ch < total;
     const int stream = l.first_stream + (int)(live ? ch >> 1 : 0), ear = (int)(ch & 1);
-    const EqProgram *prog = l.from;
+    const EqProgram *prog = l.prog;
     const double pre = prog->preamp_linear;
     double b0 = 0, b1 = 0, b2 = 0, a1 = 0, a2 = 0, z1 = 0, z2 = 0;
-    double *zp = zstate + ((((size_t)stream * 2 + l.from_voice) * 2 + ear) * 64 + (live ? f : 0)) * 2;
+    double *zp = zstate + ((((size_t)stream * 2 + l.voice) * 2 + ear) * 64 + (live ? f : 0)) * 2;
     if (live) {
         b0 = prog->coef[f][0]; b1 = prog->coef[f][1]; b2 = prog->coef[f][2]; a1 = prog->coef[f][3]; a2 = prog->coef[f][4];
         z1 = zp[0]; z2 = zp[1];
@@ -278,13 +290,13 @@ __global__ void __launch_bounds__(128) k_eq_systolic(const EqLaunch l, int gw, d
     const int chunk = (kPerWarp / groups) & ~31;            // frames per channel staged at a time (a multiple of 32)
     double *mine = stage_s[wid] + (g < groups ? g : 0) * chunk;
     const bool first = f == 0, last_f = f == gw - 1;
-    for (int c0 = 0; c0 < l.seg_len; c0 += chunk) {
-        const int cl = min(chunk, l.seg_len - c0);
+    for (int c0 = 0; c0 < a.seg_len; c0 += chunk) {
+        const int cl = min(chunk, a.seg_len - c0);
         // coalesced load, one channel at a time; the float -> double conversion and the preamp (:66) happen here, in parallel,
         // instead of on the serial path below
         for (int q = 0; q < groups && ch0 + q < total; ++q) {
             const long long cq = ch0 + q;
-            const float *src = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + l.seg_start + c0;
+            const float *src = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + a.seg_start + c0;
             for (int i = lane; i < cl; i += 32) stage_s[wid][q * chunk + i] = __dmul_rn((double)src[i], pre);
         }
         __syncwarp();
@@ -310,7 +322,7 @@ __global__ void __launch_bounds__(128) k_eq_systolic(const EqLaunch l, int gw, d
         __syncwarp();
         for (int q = 0; q < groups && ch0 + q < total; ++q) {                       // :88-89, coalesced
             const long long cq = ch0 + q;
-            float *dst = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + l.seg_start + c0;
+            float *dst = io.ptr + (l.first_stream + (cq >> 1)) * io.ss + (cq & 1) * io.cs + a.seg_start + c0;
             for (int i = lane; i < cl; i += 32) dst[i] = (float)stage_s[wid][q * chunk + i];
         }
         __syncwarp();
@@ -327,14 +339,32 @@ static cudaError_t launch_eq_t(const EqLaunch &l, double *z, StridedOut io, cuda
     return cudaGetLastError();
 }
 
+cudaError_t launch_eq_steady(const EqSegment *segs, int n_segs, int seg_start, int seg_len, double *z, StridedOut io, cudaStream_t st)
+{
+    if (n_segs <= 0 || seg_len <= 0) return cudaSuccess;
+    if (n_segs > kEqMaxSegments) return cudaErrorInvalidValue;
+    EqSteadyArgs a;
+    memset(&a, 0, sizeof(a));
+    int warps = 0;
+    for (int i = 0; i < n_segs; ++i) {
+        if (segs[i].n_filters < 1 || segs[i].n_filters > 32) return cudaErrorInvalidValue;
+        a.seg[i] = segs[i];
+        a.seg[i].warp0 = warps;
+        const int groups = 32 / segs[i].n_filters;
+        warps += (segs[i].n_streams * 2 + groups - 1) / groups;
+    }
+    if (warps == 0) return cudaSuccess;
+    a.n_segs = n_segs; a.seg_start = seg_start; a.seg_len = seg_len; a.total_warps = warps;
+    k_eq_systolic<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(a, z, io);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_eq(const EqLaunch &l, int max_filters, double *z, StridedOut io, cudaStream_t st)
 {
     if (l.n_streams <= 0 || l.seg_len <= 0) return cudaSuccess;
     if (l.to == nullptr && max_filters >= 1 && max_filters <= 32) {   // max_filters = the active state's filter count here
-        const int groups = 32 / max_filters;
-        const long long warps = ((long long)l.n_streams * 2 + groups - 1) / groups;
-        k_eq_systolic<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(l, max_filters, z, io);
-        return cudaGetLastError();
+        EqSegment seg{l.first_stream, l.n_streams, max_filters, l.from_voice, 0, 0, l.from};
+        return launch_eq_steady(&seg, 1, l.seg_start, l.seg_len, z, io, st);
     }
     if (max_filters <= 4) return launch_eq_t<4>(l, z, io, st);
     if (max_filters <= 8) return launch_eq_t<8>(l, z, io, st);

@@ -72,6 +72,17 @@ struct EqLaunch {
 };
 // z: [stream][voice(2)][ear(2)][filter(64)][2] doubles; io: planar stereo in place.
 cudaError_t launch_eq(const EqLaunch &l, int max_filters, double *z, StridedOut io, cudaStream_t st);
+// Steady-state cascades (no crossfade, 1..32 filters) of up to kEqMaxSegments stream ranges in ONE launch: per-device
+// profiles give every range its own equalizer (DeviceProfileManager.swift:4-12).
+struct EqSegment {
+    int first_stream, n_streams;
+    int n_filters, voice;
+    int warp0;              // filled in by the launcher: first warp of this range
+    int pad;
+    const EqProgram *prog;
+};
+constexpr int kEqMaxSegments = 64;
+cudaError_t launch_eq_steady(const EqSegment *segs, int n_segs, int seg_start, int seg_len, double *z, StridedOut io, cudaStream_t st);
 cudaError_t launch_eq_reset(double *z, int first_stream, int n_streams, int voice_mask, cudaStream_t st);
 
 // KF: K2 + K3 + K4 fused for a tile of `tile` (1, 2 or 4) streams per CTA; 64 <= B <= 512.

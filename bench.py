@@ -44,8 +44,9 @@ WORKLOADS = {
     "C3": ("7.1->binaural, synthetic 65,536-tap BRIR, B=512, 1024 streams/GPU", 8, 512, 1024, "synthetic65536"),
     "C4": ("full chain: 7.1->binaural with StageSH1.0 relabelled 44.1 kHz and resampled to 48 kHz (4320 -> 4702 taps), B=256, "
            "+ 10-band parametric EQ (CCA CRA fixture), 8192 streams/GPU", 8, 256, 8192, "StageSH1.0@44100"),
-    "F3": ("per-device profiles at batch scale (SURVEY.md 8(f3)): 4096 streams in 64 ranges bound alternately to the RoomSH1.0 and "
-           "StageSH1.0 banks, 7.1->binaural, B=256", 8, 256, 4096, "RoomSH1.0+StageSH1.0"),
+    "F3": ("per-device profiles at batch scale (SURVEY.md 8(f3)): 4096 streams in 64 ranges, each bound to one of two HRIR banks "
+           "(RoomSH1.0 / StageSH1.0) and one of two equalizers (CCA CRA fixture / Bass Booster), 7.1->binaural, B=256",
+           8, 256, 4096, "RoomSH1.0+StageSH1.0"),
     "C5-64": ("7.1->binaural, RoomSH1.0, B=64, 2048 streams/GPU", 8, 64, 2048, "RoomSH1.0"),
     "C5-128": ("7.1->binaural, RoomSH1.0, B=128, 2048 streams/GPU", 8, 128, 2048, "RoomSH1.0"),
     "C5-512": ("7.1->binaural, RoomSH1.0, B=512, 2048 streams/GPU", 8, 512, 2048, "RoomSH1.0"),
@@ -299,6 +300,15 @@ def run_ours(args):
     if eq_def is not None:                    # full chain: spatial -> EQ (AudioEffectGraph.swift:195-210)
         eng.eq_prepare(eq_def)
         eq_filters = sum(1 for f in eq_def["filters"] if f.get("isEnabled", True))
+    if args.workload == "F3":                 # a profile = (HRIR preset, EQ preset): every range also gets one of two equalizers
+        defs = []
+        for name in ("CCA CRA ParametricEq.txt", "Bass Booster.txt"):
+            with open(os.path.join(GOLDEN, "eq", name), "rb") as f:
+                defs.append(aw.EqualizerAPOParser.parse(f.read(), name))
+        ranges = 64
+        per = n // ranges
+        for r in range(ranges):
+            eng.eq_prepare(defs[(r // 2) % 2], r * per, per if r < ranges - 1 else n - r * per)
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
 
     # device-resident synthetic input: a time-contiguous ring of R blocks per (stream, speaker)

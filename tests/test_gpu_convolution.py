@@ -363,3 +363,17 @@ def test_fft_plan_cache(aw):
     aw.FFTSetupManager.getSetup(9)
     count, sizes = aw.FFTSetupManager.getCacheStats()
     assert 512 in sizes and count == len(sizes) == len(set(sizes))
+
+
+def test_device_synthetic_input_is_the_oracles_generator(aw):
+    """bench.py fills its device-resident input with aw_synth_fill_device and times the CPU baseline on oracle.synth_fill
+    (counter-based generator keyed (seed, stream, speaker, frame)): both must be the same data, bit for bit."""
+    torch = pytest.importorskip("torch")
+    n, S, frames, first, frame0 = 5, 8, 777, 1234, 100000
+    buf = torch.empty((n, S, frames), dtype=torch.float32, device="cuda:0")
+    aw._lib.check(aw.lib().aw_synth_fill_device(0, buf.data_ptr(), first, n, S, frame0, frames, SEED, None))
+    torch.cuda.synchronize()
+    got = buf.cpu().numpy()
+    want = oracle.synth_block(SEED, range(first, first + n), S, frame0, frames)
+    assert np.array_equal(got, want)
+    assert np.abs(got).max() <= 0.25 and got.std() > 0.1      # uniform in [-0.25, 0.25]
