@@ -1,3 +1,4 @@
 #!/bin/bash
-PYTEST_TIMEOUT=600 bash tools/gpu_check.sh
-timeout 300 bash tools/bench_all.sh F3 C4
+timeout 200 python -m pytest tests/test_gpu_eq.py -m gpu -x -q --timeout 60 2>&1 | tail -2
+timeout 200 python -m pytest tests/test_gpu_fullsize.py -m gpu -x -q -k "c4 or fused_eq" --timeout 120 2>&1 | tail -2
+timeout 300 bash tools/bench_all.sh C4 F3

@@ -3,7 +3,7 @@
 # one `ncu --set full` capture per dominant kernel.  Reports land in gpurun_out/; tools/ncu_summary.py reads them on the CPU box.
 R=${1:-r01}
 mkdir -p gpurun_out
-bash tools/bench_all.sh C2 C1 C3 C4 C5-64 C5-128 C5-512 C5-1024 C5-2048 C5-4096 | tee gpurun_out/${R}_bench_all.txt
+bash tools/bench_all.sh C2 C1 C3 C4 C5-64 C5-128 C5-512 C5-1024 C5-2048 C5-4096 F3 | tee gpurun_out/${R}_bench_all.txt
 # launch list of the default bench command: skip the 40 warm-up launches (+ set-up kernels), list 40 launches of the timed region
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 40 --csv --log-file gpurun_out/${R}_launches_C2.csv python bench.py --steps 100 --warmup 40 --no-cpu --e2e-steps 3 > gpurun_out/ncu_launches_C2.log 2>&1; echo "launch list C2 rc=$?"
 # C4 launches two kernels per step (KP + EQ): warm-up = 80 launches + set-up
