@@ -116,7 +116,9 @@ def measured_peaks():
 
 
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 100 ms from before the warm-up (so that it is already running when a short timed region starts);
+    stop(t0, t1) keeps the samples whose timestamps fall inside the timed region."""
+    QUERY = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
@@ -131,7 +133,7 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self) -> dict:
+    def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -143,18 +145,47 @@ class ClockSampler:
         self.file.flush()
         rows = [r.strip().split(",") for r in open(self.file.name).read().splitlines() if r.strip()]
         os.unlink(self.file.name)
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        inside, every = [], []
         for r in rows:
             try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
+                stamp = time.mktime(time.strptime(r[0].strip().split(".")[0], "%Y/%m/%d %H:%M:%S")) + float("0." + r[0].strip().split(".")[1])
+                rec = (float(r[2]), float(r[3]), [n for n, v in zip(names, r[6:10]) if v.strip().lower().startswith("active")])
             except Exception:
                 continue
-            for name, v in zip(names, r[5:9]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+            every.append(rec)
+            if t0 - 0.1 <= stamp <= t1 + 0.1:
+                inside.append(rec)
+        # a timed region shorter than the sampling period may catch no sample: fall back to the samples taken under the same load
+        # during the warm-up that precedes it, and say so
+        used, window = (inside, "timed region") if inside else (every[-3:], "warm-up + timed region (timed region shorter than the sampling period)")
+        sm = [u[0] for u in used]
+        reasons = sorted({n for u in used for n in u[2]})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(u[1] for u in used) if used else None,
+                "reasons": reasons, "samples": len(sm), "window": window}
+
+
+def pin_to_gpu_numa_node(gpu_index: int):
+    """Binds this rank to the CPU cores nvidia-smi reports as local to its GPU (pinned host buffers then live on that NUMA node:
+    the end-to-end path is PCIe/host-memory bound).  Returns a description, or None when the topology cannot be read."""
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+        header = next(l for l in out.splitlines() if "CPU Affinity" in l)
+        cols = [c.strip() for c in header.split("\t")]
+        col = cols.index("CPU Affinity")
+        row = next(l for l in out.splitlines() if l.startswith(f"GPU{gpu_index}\t") or l.startswith(f"GPU{gpu_index} "))
+        spec = [c.strip() for c in row.split("\t")][col]
+        cpus = set()
+        for part in spec.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return spec
+    except Exception:
+        pass
+    return None
 
 
 def cpu_filters(S, pcm, rate, l_idx, r_idx):
@@ -271,6 +302,7 @@ def run_ours(args):
     if not torch.cuda.is_available() or aw.device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
+    affinity = pin_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -323,26 +355,31 @@ def run_ours(args):
         eng.process_device(xp + 4 * (j % R) * B, S * R * B, R * B, yp, 2 * B, B, B)
 
     W = max(args.warmup, 3)
+    sampler = ClockSampler(local)
+    sampler.start()
     for j in range(W):
         step(j)
     torch.cuda.synchronize()
 
     K = args.steps
     events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
-    sampler = ClockSampler(local)
-    c0 = eng.counters()
+    for j in range(W):                       # keep the load on while nvidia-smi comes up (short timed regions)
+        step(j)
+    torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
-    sampler.start()
+    c0 = eng.counters()
+    t_start = time.time()
     events[0].record(stream)
     for j in range(K):
         step(W + j)
         events[j + 1].record(stream)
     torch.cuda.synchronize()
+    t_end = time.time()
     if dist is not None:
         dist.barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_start, t_end)
     c1 = eng.counters()
     elapsed_ms = events[0].elapsed_time(events[K])
     per_step = sorted(events[j].elapsed_time(events[j + 1]) for j in range(K))
@@ -432,6 +469,7 @@ def run_ours(args):
                     "synchronised on both sides, max over ranks; copies overlap kernels across steps (2 staging sets)",
                     "checksum": checksum},
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
+            "host_affinity": affinity,
             "clocks": clocks,
         }
         if cpu is not None:
