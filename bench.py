@@ -362,7 +362,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     K = args.steps
-    events = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for j in range(W):                       # keep the load on while nvidia-smi comes up (short timed regions)
         step(j)
     torch.cuda.synchronize()
@@ -371,18 +371,27 @@ def run_ours(args):
     torch.cuda.synchronize()
     c0 = eng.counters()
     t_start = time.time()
-    events[0].record(stream)
-    for j in range(K):
+    ev_start.record(stream)
+    for j in range(K):                       # exactly K steps back to back: nothing but the engine's launches between the two events
         step(W + j)
-        events[j + 1].record(stream)
+    ev_end.record(stream)
     torch.cuda.synchronize()
     t_end = time.time()
     if dist is not None:
         dist.barrier()
     clocks = sampler.stop(t_start, t_end)
     c1 = eng.counters()
-    elapsed_ms = events[0].elapsed_time(events[K])
-    per_step = sorted(events[j].elapsed_time(events[j + 1]) for j in range(K))
+    elapsed_ms = ev_start.elapsed_time(ev_end)
+    # per-block latency distribution: a separate pass with an event after every step (the events would otherwise sit between
+    # the launches of the timed region)
+    KL = min(K, 1000)
+    events = [torch.cuda.Event(enable_timing=True) for _ in range(KL + 1)]
+    events[0].record(stream)
+    for j in range(KL):
+        step(W + K + j)
+        events[j + 1].record(stream)
+    torch.cuda.synchronize()
+    per_step = sorted(events[j].elapsed_time(events[j + 1]) for j in range(KL))
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -393,7 +402,7 @@ def run_ours(args):
     prof_steps = min(K, 200)
     eng.profile_begin(prof_steps)
     for j in range(prof_steps):
-        step(W + K + j)
+        step(W + K + KL + j)
     prof = eng.profile_end()
     peak, peak_src = measured_peaks()
     plan = eng.plan()
