@@ -48,6 +48,11 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int R = C < 128 ? 128 / C : 1;          // rows side by side in a MAC set (one per C threads)
     static constexpr int RT = LOG2M <= 8 ? 2 : 1;            // rows per MAC thread
     static constexpr int RS = R * RT;                        // rows ((speaker, partition) pairs, consecutive partitions) per stage
+    // Where does a speaker's head row (p = 0) go?  Wide stages (B <= 128: 8 or 4 rows) would waste a whole stage on it, so there it
+    // rides in the speaker's last history stage: rows are walked in ring-slot order head+1, ..., head+P-1, head (consecutive
+    // slots), i.e. partitions 1..P-1 then 0.  From B = 256 the heads are the last S stages of the tile, as late as possible, so
+    // that a launch's first tile never waits for its forward transforms.
+    static constexpr bool MERGED = RS >= 4;
     // sets of 128 MAC threads; set q drains the ring slots q, q + MAC_SETS, ...  From B = 1024 the transforms, not the MAC, set the
     // pace (P is small, 10 transforms of 2B points per stream and block): one MAC set, and the threads go to the FFT warps.
     static constexpr int MAC_SETS = LOG2M >= 10 ? 1 : 2;
@@ -105,7 +110,7 @@ struct TileCtx {                 // what a role needs to know about the tile it 
     const float *bank_ny;
 };
 
-template <int T, int RS>
+template <int T, int RS, bool MERGED>
 __device__ __forceinline__ TileCtx tile_ctx(const PersistArgs &a, int tile)
 {
     int i = 0;
@@ -116,7 +121,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PersistArgs &a, int tile)
     c.last = d.first_stream + d.n_streams - 1;
     c.nvalid = min(T, c.last + 1 - c.s0);
     c.S = d.S; c.P = d.P; c.head = d.head;
-    c.hs = (d.P - 1 + RS - 1) / RS;
+    c.hs = MERGED ? (d.P + RS - 1) / RS : (d.P - 1 + RS - 1) / RS;   // stages per speaker (MERGED: head row included)
     c.bank = d.bank; c.bank_ny = d.bank_ny;
     return c;
 }
@@ -144,7 +149,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    auto my_tile = [&](int lt) { return tile_ctx<T, RS>(a, (int)blockIdx.x + lt * (int)gridDim.x); };
+    constexpr bool MERGED = PG::MERGED;
+    auto my_tile = [&](int lt) { return tile_ctx<T, RS, MERGED>(a, (int)blockIdx.x + lt * (int)gridDim.x); };
 
     for (int k = tid; k < PG::TW; k += PG::THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     if (tid == 0) {
@@ -169,9 +175,14 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             int lt = 0, c = 0, s = 0, jj = 0, stage = 0;
             unsigned phase = 0;
             TileCtx tc = my_tile(0);
-            bool hist = tc.hs > 0;
+            bool hist = MERGED || tc.hs > 0;
             auto advance = [&]() {
-                if (hist) {
+                if (MERGED) {
+                    if (++jj == tc.hs) {
+                        jj = 0;
+                        if (++s == tc.S) { s = 0; if (++c == NC) { c = 0; ++lt; if (lt < my_tiles) tc = my_tile(lt); } }
+                    }
+                } else if (hist) {
                     if (++jj == tc.hs) { jj = 0; if (++s == tc.S) { s = 0; hist = false; } }
                 } else if (++s == tc.S) {
                     s = 0;
@@ -182,10 +193,12 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             };
             for (int i = 0; i < warp; ++i) advance();        // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
             while (lt < my_tiles) {
-                const int p0 = hist ? 1 + jj * RS : 0;
-                const int nrows = hist ? min(RS, tc.P - p0) : 1;
+                // rows of this stage: partitions p0, p0+1, ... (mod P: in the MERGED order the last one may be the head, p = 0)
+                const int p0 = MERGED ? 1 + jj * RS : (hist ? 1 + jj * RS : 0);
+                const int nrows = MERGED ? min(RS, tc.P - jj * RS) : (hist ? min(RS, tc.P - p0) : 1);
+                const bool has_head = MERGED ? (jj * RS + nrows == tc.P) : !hist;
                 // head rows of tile lt exist once every FFT warp has published them (a monotonic count: no phase to alias)
-                if (!hist) {
+                if (has_head) {
                     const unsigned need = (unsigned)(FFT_WARPS * (lt + 1));
                     unsigned seen;
                     do {
@@ -193,7 +206,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     } while (seen < need);
                 }
                 int slot = tc.head + p0;
-                if (slot >= tc.P) slot -= tc.P;              // modulus is partitionCount (Q4)
+                if (slot >= tc.P) slot -= tc.P;              // modulus is partitionCount (Q4); p0 = P (a lone head row) lands on `head`
                 const int n1 = min(nrows, tc.P - slot);      // rows before the ring wraps
                 mbar_wait(&empty[stage], phase ^ 1u);
                 mbar_expect_tx(&full[stage], (unsigned)(nrows * (T + 2) * C * sizeof(float4)));
@@ -201,14 +214,19 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
 #pragma unroll
                 for (int u = 0; u < T; ++u) {
                     const float4 *row = fdl4 + (size_t)min(tc.s0 + u, tc.last) * stream_stride + (size_t)s * a.P_cap * halfB + c * C;
-                    const uint64_t pol = hist ? pol_stream : pol_keep;
+                    const uint64_t pol = has_head ? pol_keep : pol_stream;
                     bulk_g2s_hint(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage], pol);
                     if (RS > 1 && n1 < nrows)
                         bulk_g2s_hint(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage], pol);
                 }
-                const float4 *frow = tc.bank + ((size_t)s * tc.P + p0) * M;
+                const float4 *frow = tc.bank + ((size_t)s * tc.P + (p0 < tc.P ? p0 : 0)) * M;
                 if (NC == 1) {                               // whole rows: both planes of RS consecutive partitions are contiguous
-                    bulk_g2s_hint(dst + T * RS * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage], pol_keep);
+                    // MERGED: the head's filter row (p = 0) is the first of the speaker's bank, not the one after p = P-1
+                    const int nf = (MERGED && has_head) ? nrows - 1 : nrows;
+                    if (nf > 0) bulk_g2s_hint(dst + T * RS * C, frow, (unsigned)(nf * 2 * C * sizeof(float4)), &full[stage], pol_keep);
+                    if (nf < nrows)
+                        bulk_g2s_hint(dst + T * RS * C + nf * 2 * C, tc.bank + (size_t)s * tc.P * M, (unsigned)(2 * C * sizeof(float4)),
+                                      &full[stage], pol_keep);
                 } else {
                     bulk_g2s_hint(dst + T * C, frow + c * C, (unsigned)(C * sizeof(float4)), &full[stage], pol_keep);
                     bulk_g2s_hint(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage], pol_keep);
@@ -230,7 +248,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         constexpr int SETS = PG::MAC_SETS;
         for (int lt = 0; lt < my_tiles; ++lt) {
             const TileCtx tc = my_tile(lt);
-            const int hs = tc.hs, head0 = tc.S * hs, spc = head0 + tc.S;   // first head stage of / stages per column chunk
+            // first head stage of / stages per column chunk (MERGED: no separate head stages)
+            const int hs = tc.hs, head0 = tc.S * hs, spc = MERGED ? head0 : head0 + tc.S;
             for (int c = 0; c < NC; ++c) {
                 int jj = hs > 0 ? m % hs : 0;                // history group of my next stage (RS > 1 only)
                 float4 aL[CW][T], aR[CW][T];
@@ -240,7 +259,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     for (int u = 0; u < T; ++u) { aL[v][u] = make_float4(0.f, 0.f, 0.f, 0.f); aR[v][u] = aL[v][u]; }
                 for (; m < spc; m += SETS) {
                     int nrows = 1;                           // head stages carry one row
-                    if (RS > 1 && m < head0) nrows = min(RS, tc.P - 1 - jj * RS);
+                    if (MERGED) nrows = min(RS, tc.P - jj * RS);
+                    else if (RS > 1 && m < head0) nrows = min(RS, tc.P - 1 - jj * RS);
                     mbar_wait(&full[stage], phase);
                     const float4 *src = ring + stage * stage_f4;
 #pragma unroll

@@ -235,17 +235,19 @@ def test_small_and_ragged_stream_counts_and_stereo_on_the_persistent_path(aw, hr
         for i in range(n):
             ref = oracle.direct_conv_f64(xu[i], h)
             assert np.abs(y[i] - ref).max() <= MAX_ABS and snr_db(ref, y[i]) >= SNR_DB, (layout, n, block, i)
-    # P = 1: a 200-tap response in one 256-frame partition
+    # P = 1 (heads only) and P = 2, 5 (stages that mix history rows with the head row at B <= 128): short responses
     lay = aw.InputLayout.stereo()
     l, r = _maps(aw, lay)
-    short = wav_o.audioData[:, :200].copy()
-    bank = aw.HRIRBank(short, FS, FS, l, r, 256)
-    assert bank.partitions == 1
-    xu, y, plan = _render_twins(aw, bank, 9, 2, 256, blocks=5, unique=9, per_call=256, pcm_lr=None)
-    hs = np.stack([np.stack([short[l[s]], short[r[s]]]) for s in range(2)])
-    for i in range(9):
-        ref = oracle.direct_conv_f64(xu[i], hs)
-        assert np.abs(y[i] - ref).max() <= MAX_ABS, i
+    for taps, block in [(200, 256), (50, 64), (100, 64), (300, 64), (120, 128), (500, 128)]:
+        short = wav_o.audioData[:, :taps].copy()
+        bank = aw.HRIRBank(short, FS, FS, l, r, block)
+        assert bank.partitions == -(-taps // block)
+        xu, y, plan = _render_twins(aw, bank, 9, 2, block, blocks=bank.partitions + 4, unique=9, per_call=block, pcm_lr=None)
+        assert plan["kernels"][0].startswith("k_persistent<"), plan
+        hs = np.stack([np.stack([short[l[s]], short[r[s]]]) for s in range(2)])
+        for i in range(9):
+            ref = oracle.direct_conv_f64(xu[i], hs)
+            assert np.abs(y[i] - ref).max() <= MAX_ABS, (taps, block, i)
 
 
 def test_fused_equalizer_epilogue_is_bit_identical_to_the_separate_pass(aw, hrtf_path, eq_fixture_bytes):
