@@ -133,6 +133,12 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def lines(self) -> int:
+        try:
+            return sum(1 for _ in open(self.file.name))
+        except Exception:
+            return 0
+
     def stop(self, t0: float, t1: float) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -158,7 +164,7 @@ class ClockSampler:
                 inside.append(rec)
         # a timed region shorter than the sampling period may catch no sample: fall back to the samples taken under the same load
         # during the warm-up that precedes it, and say so
-        used, window = (inside, "timed region") if inside else (every[-3:], "warm-up + timed region (timed region shorter than the sampling period)")
+        used, window = (inside, "timed region") if inside else (every[-3:], "same load just before/after the timed region (shorter than the sampling period)")
         sm = [u[0] for u in used]
         reasons = sorted({n for u in used for n in u[2]})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(u[1] for u in used) if used else None,
@@ -379,6 +385,14 @@ def run_ours(args):
     t_end = time.time()
     if dist is not None:
         dist.barrier()
+    if sampler.proc is not None and sampler.lines() < 2:
+        # nvidia-smi had not produced a sample yet (it takes a few hundred ms to come up on an 8-GPU box): keep the very same
+        # load running, untimed, until it has — at most 2 s
+        t_wait = time.time()
+        while sampler.lines() < 2 and time.time() - t_wait < 2.0:
+            for j in range(20):
+                step(j)
+            torch.cuda.synchronize()
     clocks = sampler.stop(t_start, t_end)
     c1 = eng.counters()
     elapsed_ms = ev_start.elapsed_time(ev_end)
