@@ -17,6 +17,7 @@
 #include "aw_kernels.h"
 
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 
@@ -263,6 +264,10 @@ __global__ void __launch_bounds__(128) k_eq_systolic(const __grid_constant__ EqS
 {
     constexpr int kPerWarp = 1024;                          // doubles of staging per warp (>= 32 frames for each of up to 32 channels)
     __shared__ double stage_s[4][kPerWarp];                 // per warp: `groups` channels x `chunk` frames, staged coalesced
+    // programmatic dependent launch (see k_persistent): the block kernel of the next call may be scheduled as this grid retires;
+    // nothing is read before the convolution that feeds this equalizer has completed
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int gwarp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (gwarp >= a.total_warps) return;
@@ -355,8 +360,17 @@ cudaError_t launch_eq_steady(const EqSegment *segs, int n_segs, int seg_start, i
     }
     if (warps == 0) return cudaSuccess;
     a.n_segs = n_segs; a.seg_start = seg_start; a.seg_len = seg_len; a.total_warps = warps;
-    k_eq_systolic<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(a, z, io);
-    return cudaGetLastError();
+    static const bool pdl = !(getenv("AW_PDL") && atoi(getenv("AW_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((warps + 3) / 4));
+    cfg.blockDim = dim3(128);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_eq_systolic, a, z, io);
 }
 
 cudaError_t launch_eq(const EqLaunch &l, int max_filters, double *z, StridedOut io, cudaStream_t st)

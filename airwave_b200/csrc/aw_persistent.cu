@@ -28,6 +28,7 @@
 // Stage order inside a tile (and column chunk): for every speaker its history partitions p = 1..P-1 in groups of RS, then
 // the S head rows — the same for every tile size and stream count, so a stream's output does not depend on how many
 // streams the engine renders or on which GPU it lives.
+#include <stdlib.h>
 #include <string.h>
 
 #include "aw_fft_blocks.cuh"
@@ -161,6 +162,11 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // Programmatic dependent launch: the next block's launch may be scheduled onto SMs as this grid's CTAs retire (its prologue
+    // above touches nothing a previous launch writes), and this grid goes no further until the previous one has completed and
+    // flushed — the FDL head slots, the overlap buffer and the output it wrote are read/overwritten below.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp < PRODUCERS) {
         // ===== producers: warp w fills the ring slots w, w + PRODUCERS, ... every time the stage sequence comes round to them =====
@@ -556,8 +562,18 @@ cudaError_t launch_persistent_lt(const PersistArgs &a, int ctas, cudaStream_t st
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    k_persistent<LOG2M, T><<<ctas, PGeo<LOG2M, T>::THREADS, PGeo<LOG2M, T>::smem, st>>>(a);
-    return cudaGetLastError();
+    static const bool pdl = !(getenv("AW_PDL") && atoi(getenv("AW_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3((unsigned)PGeo<LOG2M, T>::THREADS);
+    cfg.dynamicSmemBytes = PGeo<LOG2M, T>::smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k_persistent<LOG2M, T>, a);
 }
 
 }  // namespace
