@@ -6,7 +6,7 @@ import collections, csv, io, json, os, re, shutil, subprocess, sys
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 os.makedirs("profiles", exist_ok=True)
 shutil.copy(f"gpurun_out/{R}_bench_all.txt", f"profiles/{R}_bench_all.txt")
-for name, skip in [("C2", 60), ("C4", 110)]:
+for name, skip in [("C2", 100), ("C4", 190)]:
     shutil.copy(f"gpurun_out/{R}_launches_{name}.csv", f"profiles/{R}_launches_{name}.csv")
     rows = [r for r in csv.reader(open(f"profiles/{R}_launches_{name}.csv")) if len(r) > 5]
     hdr = next(r for r in rows if "Kernel Name" in r)
