@@ -3,7 +3,6 @@ import os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import airwave_b200 as aw
-import oracle
 
 FS = 48000.0
 SEED = 0x41495257
@@ -22,7 +21,7 @@ def run(n, B, taps, blocks, per_call, unique=3, S=8, env=None):
     eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=per_call, max_partitions=bank.partitions)
     eng.set_bank(bank)
     frames = blocks * B
-    xu = oracle.synth_block(SEED, [101 + 7 * i for i in range(unique)], S, 0, frames)
+    xu = np.random.default_rng(SEED).uniform(-0.25, 0.25, (unique, S, frames)).astype(np.float32)
     reps = -(-n // unique)
     outs = []
     for a in range(0, frames, per_call):
