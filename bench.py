@@ -101,8 +101,9 @@ def speaker_maps(S: int):
 
 
 def algorithmic_bytes(S: int, B: int, P: int, eq_filters: int = 0) -> int:
-    """per stream per block, FDL ring (1 slot written + P-1 read) + input + output [+ EQ state]."""
-    return 8 * S * B * P + 4 * S * B + 8 * B + 32 * eq_filters
+    """per stream per block, FDL ring (1 slot written + P-1 read) + input + output [+ EQ state: 4 doubles per
+    filter read and written, which is what the table's 322,176 B for C4 contains]."""
+    return 8 * S * B * P + 4 * S * B + 8 * B + 64 * eq_filters
 
 
 def measured_peaks():
