@@ -384,6 +384,7 @@ def run_ours(args):
     ev_end.record(stream)
     torch.cuda.synchronize()
     t_end = time.time()
+    c1 = eng.counters()
     if dist is not None:
         dist.barrier()
     if sampler.proc is not None and sampler.lines() < 2:
@@ -395,7 +396,6 @@ def run_ours(args):
                 step(j)
             torch.cuda.synchronize()
     clocks = sampler.stop(t_start, t_end)
-    c1 = eng.counters()
     elapsed_ms = ev_start.elapsed_time(ev_end)
     # per-block latency distribution: a separate pass with an event after every step (the events would otherwise sit between
     # the launches of the timed region)
