@@ -8,7 +8,7 @@ bash tools/bench_all.sh C2 C1 C3 C4 C5-64 C5-128 C5-512 C5-1024 C5-2048 C5-4096 
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 40 --csv --log-file gpurun_out/${R}_launches_C2.csv python bench.py --steps 100 --warmup 40 --no-cpu --e2e-steps 3 > gpurun_out/ncu_launches_C2.log 2>&1; echo "launch list C2 rc=$?"
 # C4 launches two kernels per step (KP + EQ): warm-up = 2 x 80 launches + set-up
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 190 -c 40 --csv --log-file gpurun_out/${R}_launches_C4.csv python bench.py --workload C4 --steps 100 --warmup 40 --no-cpu --e2e-steps 3 > gpurun_out/ncu_launches_C4.log 2>&1; echo "launch list C4 rc=$?"
-for w in C2 C3 C5-512 C5-64 C5-2048; do
+for w in C2 C3 C4 C5-512 C5-64 C5-2048; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persistent -s 45 -c 1 -o gpurun_out/${R}_full_$w -f python bench.py --workload $w --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_$w.log 2>&1; echo "$w rc=$?"
 done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eq_systolic -s 45 -c 1 -o gpurun_out/${R}_full_C4eq -f python bench.py --workload C4 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_C4eq.log 2>&1; echo "C4eq rc=$?"
