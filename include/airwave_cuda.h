@@ -221,14 +221,15 @@ AW_API int aw_engine_reset(aw_engine *engine, int first, int count, int what);
 /* Counters since creation: kernels launched by this engine, blocks rendered, bytes copied H2D / D2H. */
 AW_API int aw_engine_counters(const aw_engine *engine, unsigned long long *kernel_launches, unsigned long long *blocks,
                               unsigned long long *h2d_bytes, unsigned long long *d2h_bytes);
-/* Execution plan chosen for the engine: fused_tile = streams per CTA of the fused K2+K3+K4 kernel (0 = split kernels),
- * mac_tile = streams per thread of the stand-alone K3, partitions_cap = FDL slots per (stream, speaker). */
+/* Execution plan chosen for the engine: fused_tile = streams per tile of the block kernel that does K2+K3+K4 in one launch
+ * (the persistent kernel KP, or the single-wave KF when AW_PERSISTENT=0; 0 = split kernels K2, K3, K4), mac_tile = streams per
+ * thread of the stand-alone K3, partitions_cap = FDL slots per (stream, speaker). */
 AW_API int aw_engine_plan(const aw_engine *engine, int *fused_tile, int *mac_tile, int *partitions_cap);
-/* Per-kernel device timing for benchmarks: between begin and end, CUDA events bracket the three per-block kernels
- * (K2 input_rfft, K3 fdl_cmac, K4 irfft_out) of up to `max_blocks` blocks on the engine's stream.  end() synchronises and
- * returns the summed milliseconds and launch counts per kernel (index 0..2); with the fused kernel index 0 is the whole
- * fused launch and 1..2 are zero.  Not for the real-time path. */
-AW_API int aw_engine_profile_begin(aw_engine *engine, int max_blocks);   /* kernel_ms / kernel_launches below: 4 entries, [3] = equalizer */
+/* Per-kernel device timing for benchmarks: between begin and end, CUDA events bracket the per-block kernels of up to `max_blocks`
+ * blocks on the engine's stream.  end() synchronises and returns the summed milliseconds and launch counts of 4 slots: [0..2] the
+ * kernels aw_engine_kernels() names, in that order (one-kernel plans use slot 0 only), [3] the equalizer launches of a call.
+ * Profiling serialises work that otherwise overlaps (side streams).  Not for the real-time path. */
+AW_API int aw_engine_profile_begin(aw_engine *engine, int max_blocks);
 AW_API int aw_engine_profile_end(aw_engine *engine, double *kernel_ms, unsigned long long *kernel_launches);
 /* Semicolon-separated names of the kernels the engine launches per block, in launch order (e.g. "k_persistent<8,4>"). */
 AW_API int aw_engine_kernels(const aw_engine *engine, char *names, int capacity);
