@@ -36,6 +36,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
+// Wait that is expected to last (a whole tile): back off between polls so that the waiting warps leave the issue slots — and the
+// power budget — to the warps that stream.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITR_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONER_%=;\n\t"
+        "nanosleep.u32 256;\n\t"
+        "bra WAITR_%=;\n\t"
+        "DONER_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),

@@ -207,9 +207,11 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 if (has_head) {
                     const unsigned need = (unsigned)(FFT_WARPS * (lt + 1));
                     unsigned seen;
-                    do {
+                    for (;;) {
                         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(heads_done)) : "memory");
-                    } while (seen < need);
+                        if (seen >= need) break;
+                        __nanosleep(128);
+                    }
                 }
                 int slot = tc.head + p0;
                 if (slot >= tc.P) slot -= tc.P;              // modulus is partitionCount (Q4); p0 = P (a lone head row) lands on `head`
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         if (my_tiles > 0) forward_tile(0);
         for (int lt = 0; lt < my_tiles; ++lt) {
             if (lt + 1 < my_tiles) forward_tile(lt + 1);
-            mbar_wait(acc_ready, (unsigned)(lt & 1));
+            mbar_wait_relaxed(acc_ready, (unsigned)(lt & 1));
             if (!(a.debug & 2)) inverse_tile(lt);
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);
