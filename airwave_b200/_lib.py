@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     L.aw_engine_process_device.argtypes = [vp, vp, ll, ll, vp, ll, ll, C.c_int]
     L.aw_engine_process_stereo.argtypes = [vp, vp, vp, vp, vp, C.c_int]
     L.aw_engine_submit.argtypes = [vp, vp, vp, C.c_int]
+    L.aw_engine_submit_device.argtypes = [vp, vp, ll, ll, vp, C.c_int]
     L.aw_engine_wait.argtypes = [vp]
     L.aw_engine_reset.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.aw_engine_counters.argtypes = [vp, ull, ull, ull, ull]

@@ -325,6 +325,10 @@ class BinauralEngine:
     def submit(self, in_ptr: int, out_ptr: int, frames: int) -> None:
         L.check(L.lib().aw_engine_submit(self._h, in_ptr, out_ptr, frames))
 
+    def submit_device(self, in_ptr: int, in_ss: int, in_cs: int, out_ptr: int, frames: int) -> None:
+        """Device-resident input, host output copied asynchronously (valid after wait())."""
+        L.check(L.lib().aw_engine_submit_device(self._h, in_ptr, in_ss, in_cs, out_ptr, frames))
+
     def wait(self) -> None:
         L.check(L.lib().aw_engine_wait(self._h))
 

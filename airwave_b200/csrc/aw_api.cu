@@ -104,7 +104,9 @@ struct Segment {
     int head;              // fdlIndex (ConvolutionEngine.swift:39)
 };
 
-constexpr int kEqPool = 1024;   // ParametricEqualizerState objects alive per engine (slot 0 = shared unity)
+constexpr size_t kZeroCopyBytes = 2u << 20;   // engines whose staging fits in this use mapped host buffers (no copies)
+constexpr int kEqPool = 1024;   // ParametricEqualizerState objects alive per engine at creation (slot 0 = shared unity); the pool
+                                // doubles on demand in the control path (eq_pool_grow), never in aw_engine_process*
 
 struct EqMachine {
     int first = 0, count = 0;
@@ -135,7 +137,11 @@ struct aw_engine {
     bool persistent = false;       // use the persistent warp-specialised kernel KP (aw_persistent.cu) instead of KF
     int persistentTile = 0;        // streams per tile of KP (4 or 2)
     int persistentCtas = 0;        // CTAs of KP (default: one per SM)
-    int persistentDebug = 0;       // timing experiments only (AW_PERSISTENT_DEBUG)
+    int persistentDebug = 0;       // timing experiments only (AW_PERSISTENT_DEBUG; ignored unless built with -DAW_TIMING_EXPERIMENTS)
+    int ringExtra = 0;             // spare FDL ring slots per (stream, speaker): 1 with KP (see KpSegment::Pm), else 0
+    int kpOrder = 1;               // walk order of a multi-block call's (tile, block) items: 1 = tile-major, 0 = block-major
+    int kpKeepPct = 50;            // tile-major: share of a tile's history rows kept in L2 (evict_last) for its next block
+    bool kpMultiBlock = true;      // one launch per call (AW_KP_MULTIBLOCK=0: one launch per block)
     bool eqFusion = false;         // AW_EQ_FUSION=1: steady-state EQ rides in KP's epilogue.  Off by default: the bit-exact float64
                                    // recurrence needs ~220 cycles per sample, 29 us per 256-frame block on the few FFT warps of a
                                    // CTA — longer than a tile lasts — whereas the separate K5 pass hides it behind 37 warps per SM
@@ -148,6 +154,10 @@ struct aw_engine {
     EqProgram *d_eq_prog = nullptr;
     Staging stage[2];
     int nextStage = 0;
+    // Small engines (the reference's own case: one stereo stream per callback, AudioPipeline.swift:3-11): the synchronous host entry
+    // points stage the caller's buffers in page-locked memory the kernels read and write DIRECTLY over PCIe (zero-copy) — one
+    // launch and one stream synchronisation per call instead of four driver copies around it.
+    float *h_in = nullptr, *h_out = nullptr;
     cudaStream_t stream = nullptr, h2d = nullptr, d2h = nullptr;
     // engines whose stream ranges are bound to different banks (per-device profiles, DeviceProfileManager.swift:4-12) launch one
     // grid per range; small ranges leave most SMs idle, so their grids are spread over side streams and run concurrently
@@ -165,6 +175,9 @@ struct aw_engine {
     // adapter counters (RealtimeAudioProcessor.swift:26-28)
     int pendingCount = 0, fifoReadIndex = 0, fifoCount = 0;
     unsigned long long launches = 0, blocks = 0, h2dBytes = 0, d2hBytes = 0;
+    // The host-side state of a call (FDL heads, adapter counters, equalizer state machines) advances while its launches are
+    // enqueued.  If one of them fails, host and device no longer agree: the engine refuses to render until it has been reset.
+    bool poisoned = false;
     // optional per-kernel event timing (benchmarks only)
     std::vector<cudaEvent_t> profEvents, profEqEvents;
     size_t profUsed = 0, profEqUsed = 0;
@@ -204,6 +217,7 @@ void split_segments(aw_engine *e, int at)
 }
 
 void split_machines(aw_engine *e, int at);
+int eq_pool_grow(aw_engine *e);
 
 // ---- EQ state pool ---------------------------------------------------------------------------------
 void eq_retain(aw_engine *e, int slot) { if (slot > 0) ++e->eqRef[slot]; }
@@ -231,6 +245,30 @@ void split_machines(aw_engine *e, int at)
             return;
         }
     }
+}
+
+// Doubles the device array of EqProgram slots (control path only; the render path never allocates).  Bounded by the number of
+// state objects the engine's streams can reference at once (9 references per range, at most n_streams ranges).
+int eq_pool_grow(aw_engine *e)
+{
+    const size_t cap = e->eqRef.size(), limit = (size_t)e->n * 9 + kEqPool;
+    if (cap >= limit) return set_error(AW_ERR_OUT_OF_MEMORY, "equalizer state pool exhausted");
+    const size_t grown = std::min(limit, cap * 2);
+    EqProgram *d = nullptr;
+    cudaError_t ce = cudaMalloc(&d, sizeof(EqProgram) * grown);
+    if (ce != cudaSuccess) { cudaGetLastError(); return set_error(AW_ERR_OUT_OF_MEMORY, "equalizer state pool: cudaMalloc failed"); }
+    // nothing may still be reading the old array: the engine's streams are idle after this
+    ce = cudaStreamSynchronize(e->stream);
+    for (int k = 0; k < aw_engine::kSideStreams && ce == cudaSuccess; ++k) ce = cudaStreamSynchronize(e->side[k]);
+    if (ce == cudaSuccess) ce = cudaMemcpy(d, e->d_eq_prog, sizeof(EqProgram) * cap, cudaMemcpyDeviceToDevice);
+    if (ce == cudaSuccess) ce = cudaMemset(d + cap, 0, sizeof(EqProgram) * (grown - cap));
+    if (ce != cudaSuccess) { cudaFree(d); return set_error(AW_ERR_CUDA, std::string("equalizer state pool: ") + cudaGetErrorString(ce)); }
+    cudaFree(e->d_eq_prog);
+    e->d_eq_prog = d;
+    e->eqRef.resize(grown, 0);
+    e->eqFilters.resize(grown, 0);
+    e->eqPreamp.resize(grown, 1.0);
+    return AW_OK;
 }
 
 // ParametricEqualizerProcessor.prepare (ParametricEqualizerProcessor.swift:174-217): validates, designs the biquads and
@@ -270,8 +308,13 @@ int eq_prepare_state(aw_engine *e, double preampDB, const aw_eq_filter *filters,
     }
     prog.n_filters = k;
     int s = -1;
-    for (int i = 1; i < kEqPool; ++i) if (e->eqRef[i] == 0) { s = i; break; }
-    if (s < 0) return set_error(AW_ERR_OUT_OF_MEMORY, "equalizer state pool exhausted");
+    for (int i = 1; i < (int)e->eqRef.size(); ++i) if (e->eqRef[i] == 0) { s = i; break; }
+    if (s < 0) {
+        // every stream range may hold several live state objects (active, transition target, pending, retired): grow
+        s = (int)e->eqRef.size();
+        const int rc = eq_pool_grow(e);
+        if (rc != AW_OK) return rc;
+    }
     AW_CUDA(cudaMemcpyAsync(e->d_eq_prog + s, &prog, sizeof(prog), cudaMemcpyHostToDevice, e->stream));
     AW_CUDA(cudaStreamSynchronize(e->stream));
     e->eqRef[s] = 1;
@@ -427,18 +470,23 @@ int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
     return AW_OK;
 }
 
-// ---- one block of UPOLS for every rendering segment ----------------------------------------------------
-int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap, StridedOut out, const EqFuse &eq)
+// ---- nb blocks of UPOLS for every rendering segment (nb > 1: KP only) ------------------------------------------------
+int ring_modulus(const aw_engine *e, const aw_bank *b) { return b->P + e->ringExtra; }
+
+int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap, StridedOut out, const EqFuse &eq, int nb = 1)
 {
+    // fdlIndex of the first block of this call (ConvolutionEngine.swift:256-259); it moves down once per block
     for (Segment &seg : e->segments) {
         if (!seg.bank) continue;
-        seg.head -= 1;                                   // ConvolutionEngine.swift:256-259
-        if (seg.head < 0) seg.head += seg.bank->P;
+        seg.head -= 1;
+        if (seg.head < 0) seg.head += ring_modulus(e, seg.bank);
     }
     const bool literal = (e->cfg.flags & AW_ENGINE_LITERAL_STEREO) != 0;   // RealtimeAudioProcessor.swift:145
     if (e->persistent) {
-        // KP: ONE launch walks the tiles of every range (up to kKpMaxSegments per launch), whatever bank each is bound to
+        // KP: ONE launch walks the tiles of every range (up to kKpMaxSegments per launch), whatever bank each is bound to, and
+        // the nb blocks of the call
         KpSegment segs[kKpMaxSegments];
+        const KpCall call{nb, e->kpOrder, e->kpKeepPct, e->persistentDebug};
         size_t i = 0;
         while (i < e->segments.size()) {
             int n = 0;
@@ -450,8 +498,10 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
                 k.n_streams = seg.count;
                 k.S = literal ? std::min(seg.bank->S, 2) : seg.bank->S;
                 k.P = seg.bank->P;
+                k.Pm = ring_modulus(e, seg.bank);
                 k.head = seg.head;
                 k.tile0 = 0;
+                k.n_big = 0;
                 k.bank = seg.bank->d_bank;
                 k.bank_ny = seg.bank->d_ny;
             }
@@ -460,12 +510,20 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
             cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
             if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
             AW_LAUNCH(e, launch_persistent(segs, n, e->S, e->P_cap, e->log2m, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl,
-                                           e->d_fdl_ny, out, e->d_tw, e->persistentTile, e->persistentCtas, e->persistentDebug, eq, e->stream));
+                                           e->d_fdl_ny, out, e->d_tw, e->persistentTile, e->persistentCtas, call, eq, e->stream));
             if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
         }
-        ++e->blocks;
+        // the remaining nb - 1 decrements of fdlIndex
+        for (Segment &seg : e->segments) {
+            if (!seg.bank || nb <= 1) continue;
+            const int pm = ring_modulus(e, seg.bank);
+            seg.head -= (nb - 1) % pm;
+            if (seg.head < 0) seg.head += pm;
+        }
+        e->blocks += (unsigned long long)nb;
         return AW_OK;
     }
+    if (nb != 1) return set_error(AW_ERR_UNSUPPORTED, "multi-block launches need the persistent kernel");
     int rendering = 0;
     for (const Segment &seg : e->segments) rendering += seg.bank != nullptr;
     // KF / split kernels, several ranges: fork the block onto the side streams (round-robin), join before anything else touches
@@ -490,6 +548,7 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         g.B = e->B;
         g.log2m = e->log2m;
         g.P = b->P;
+        g.Pm = 0;
         g.P_cap = e->P_cap;
         g.head = seg.head;
         const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
@@ -526,10 +585,22 @@ bool any_rendering(const aw_engine *e)
 }
 
 // RealtimeAudioProcessor.process (RealtimeAudioProcessor.swift:77-119) + AudioEffectGraph routing (:179-246), device side.
+int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, bool dup_mono);
+
 int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, bool dup_mono)
 {
     if (frames <= 0) return AW_OK;                                              // :84
     if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");   // :85
+    if (e->poisoned)
+        return set_error(AW_ERR_NOT_READY, "a launch of an earlier call failed, engine state is undefined: call aw_engine_reset on the "
+                                           "whole engine (AW_RESET_SPATIAL | AW_RESET_EQ) first");
+    const int rc = process_device_body(e, in, out, frames, dup_mono);
+    if (rc != AW_OK) e->poisoned = true;   // heads / counters / EQ transitions may have advanced past what the device executed
+    return rc;
+}
+
+int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, bool dup_mono)
+{
     const int B = e->B;
     const EqFuse no_eq{nullptr, nullptr, 0, 0};
     // the equalizer's per-call bookkeeping (target observation, retirement, reset) does not depend on the samples: do it first,
@@ -551,12 +622,19 @@ int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, 
             const int nb = frames / B;
             if (e->eqFusion && e->segments.size() == 1 && e->machines.size() == 1) eq_fusable(e, e->machines[0], &fused);
             StridedIn ov{e->d_overlap, (long long)e->S * B, (long long)B};
-            for (int b = 0; b < nb; ++b) {
-                StridedIn cur{in.ptr + (size_t)b * B, in.ss, in.cs};
-                StridedIn prev = b == 0 ? ov : StridedIn{in.ptr + (size_t)(b - 1) * B, in.ss, in.cs};
-                StridedOut o{out.ptr + (size_t)b * B, out.ss, out.cs, 0, 0};
-                const int rc = process_block(e, cur, prev, b == nb - 1, o, fused);
+            if (e->persistent && e->kpMultiBlock && fused.n_filters == 0) {
+                // KP walks the nb blocks of the call in one launch: block b's frame is [block b-1 | block b] of `in` (the engine's
+                // overlap buffer before block 0), and only the call's last block is parked for the next call
+                const int rc = process_block(e, in, ov, true, out, no_eq, nb);
                 if (rc != AW_OK) return rc;
+            } else {
+                for (int b = 0; b < nb; ++b) {
+                    StridedIn cur{in.ptr + (size_t)b * B, in.ss, in.cs};
+                    StridedIn prev = b == 0 ? ov : StridedIn{in.ptr + (size_t)(b - 1) * B, in.ss, in.cs};
+                    StridedOut o{out.ptr + (size_t)b * B, out.ss, out.cs, 0, 0};
+                    const int rc = process_block(e, cur, prev, b == nb - 1, o, fused);
+                    if (rc != AW_OK) return rc;
+                }
             }
         } else {
             int inputOffset = 0;
@@ -650,6 +728,8 @@ void free_engine(aw_engine *e)
         if (s.compute_done) cudaEventDestroy(s.compute_done);
         if (s.out_done) cudaEventDestroy(s.out_done);
     }
+    if (e->h_in) cudaFreeHost(e->h_in);
+    if (e->h_out) cudaFreeHost(e->h_out);
     for (cudaEvent_t ev : e->profEvents) cudaEventDestroy(ev);
     for (cudaEvent_t ev : e->profEqEvents) cudaEventDestroy(ev);
     for (int k = 0; k < aw_engine::kSideStreams; ++k) {
@@ -958,6 +1038,14 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         AW_TRY(cudaEventCreateWithFlags(&e->stage[i].compute_done, cudaEventDisableTiming));
         AW_TRY(cudaEventCreateWithFlags(&e->stage[i].out_done, cudaEventDisableTiming));
     }
+    {
+        const char *zc_env = getenv("AW_ZERO_COPY");   // 0 = always stage through device memory with copies (comparisons)
+        const size_t in_bytes = n * S * maxFrames * sizeof(float), out_bytes = n * 2 * maxFrames * sizeof(float);
+        if (in_bytes + out_bytes <= kZeroCopyBytes && !(zc_env && atoi(zc_env) == 0)) {
+            AW_TRY(cudaHostAlloc(&e->h_in, in_bytes, cudaHostAllocMapped));
+            AW_TRY(cudaHostAlloc(&e->h_out, out_bytes, cudaHostAllocMapped));
+        }
+    }
     // unity program in slot 0 (ParametricEqualizerProcessor.unityState, :128,158)
     EqProgram unity;
     memset(&unity, 0, sizeof(unity));
@@ -1001,6 +1089,10 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         e->persistentDebug = d_env ? atoi(d_env) : 0;
         const char *q_env = getenv("AW_EQ_FUSION");
         e->eqFusion = q_env && atoi(q_env) != 0;
+        e->ringExtra = e->persistent ? 1 : 0;
+        if (const char *v = getenv("AW_KP_ORDER")) e->kpOrder = atoi(v) != 0;
+        if (const char *v = getenv("AW_KP_KEEP")) e->kpKeepPct = std::max(0, std::min(100, atoi(v)));
+        if (const char *v = getenv("AW_KP_MULTIBLOCK")) e->kpMultiBlock = atoi(v) != 0;
         if (e->persistent) {
             // largest tile (most filter reuse) unless the smaller one loses clearly less to round quantisation
             auto eff = [&](int T) {
@@ -1037,7 +1129,7 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         }
     }
     if (config->max_partitions > 0) {
-        rc = alloc_fdl(e, config->max_partitions);
+        rc = alloc_fdl(e, config->max_partitions + e->ringExtra);
         if (rc != AW_OK) return fail(rc);
     }
 #undef AW_TRY
@@ -1055,8 +1147,8 @@ extern "C" int aw_engine_set_bank(aw_engine *e, int first, int count, const aw_b
     if (bank) {
         if (bank->device != e->cfg.device || bank->B != e->B) return set_error(AW_ERR_MISMATCH, "bank device/block size differ from the engine's");
         if (bank->S > e->S) return set_error(AW_ERR_MISMATCH, "bank has more speakers than the engine has input channels");
-        if (!e->d_fdl) { if ((rc = alloc_fdl(e, bank->P)) != AW_OK) return rc; }
-        if (bank->P > e->P_cap) return set_error(AW_ERR_MISMATCH, "bank has more partitions than the engine's max_partitions");
+        if (!e->d_fdl) { if ((rc = alloc_fdl(e, bank->P + e->ringExtra)) != AW_OK) return rc; }
+        if (bank->P + e->ringExtra > e->P_cap) return set_error(AW_ERR_MISMATCH, "bank has more partitions than the engine's max_partitions");
     }
     AW_CUDA(cudaStreamSynchronize(e->stream));
     split_segments(e, first);
@@ -1071,11 +1163,13 @@ extern "C" int aw_engine_set_bank(aw_engine *e, int first, int count, const aw_b
         else ++i;
     }
     if ((rc = clear_spatial_state(e, first, count)) != AW_OK) return rc;        // fresh engines: zero overlap + FDL
-    if (first == 0 && count == e->n) {                                          // new RealtimeAudioProcessor: empty FIFO
-        e->pendingCount = 0; e->fifoReadIndex = 0; e->fifoCount = 0;
-        AW_CUDA(cudaMemsetAsync(e->d_pending, 0, (size_t)e->n * e->S * e->B * sizeof(float), e->stream));
-        AW_CUDA(cudaMemsetAsync(e->d_fifo, 0, (size_t)e->n * 2 * e->fifoCap * sizeof(float), e->stream));
-    }
+    // a new RealtimeAudioProcessor starts with empty pending/FIFO buffers (RealtimeAudioProcessor.swift:41-61): the rows of the
+    // re-bound range are cleared, so nothing rendered with the previous bank (or never written, for a passthrough range) is
+    // drained.  The adapter COUNTERS are engine-wide (all streams advance in lock-step): a range re-bound in
+    // the middle of a block shares the engine's phase and emits silence for what would have been buffered samples.
+    AW_CUDA(cudaMemsetAsync(e->d_pending + (size_t)first * e->S * e->B, 0, (size_t)count * e->S * e->B * sizeof(float), e->stream));
+    AW_CUDA(cudaMemsetAsync(e->d_fifo + (size_t)first * 2 * e->fifoCap, 0, (size_t)count * 2 * e->fifoCap * sizeof(float), e->stream));
+    if (first == 0 && count == e->n) { e->pendingCount = 0; e->fifoReadIndex = 0; e->fifoCount = 0; }
     AW_CUDA(cudaStreamSynchronize(e->stream));
     return AW_OK;
 }
@@ -1213,6 +1307,17 @@ extern "C" int aw_engine_process(aw_engine *e, const float *in, float *out, int 
     DeviceGuard guard(e->cfg.device);
     Staging &s = e->stage[0];
     const size_t inBytes = (size_t)e->n * e->S * frames * sizeof(float), outBytes = (size_t)e->n * 2 * frames * sizeof(float);
+    if (e->h_in) {   // zero-copy: the kernels read the staged input and write the output over PCIe themselves
+        memcpy(e->h_in, in, inBytes);
+        const int zrc = process_device_impl(e, StridedIn{e->h_in, (long long)e->S * frames, (long long)frames},
+                                            StridedOut{e->h_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
+        if (zrc != AW_OK) return zrc;
+        AW_CUDA(cudaStreamSynchronize(e->stream));
+        memcpy(out, e->h_out, outBytes);
+        e->h2dBytes += inBytes;
+        e->d2hBytes += outBytes;
+        return AW_OK;
+    }
     AW_CUDA(cudaMemcpyAsync(s.d_in, in, inBytes, cudaMemcpyHostToDevice, e->stream));
     const int rc = process_device_impl(e, StridedIn{s.d_in, (long long)e->S * frames, (long long)frames},
                                        StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
@@ -1234,6 +1339,21 @@ extern "C" int aw_engine_process_stereo(aw_engine *e, const float *input_left, c
     DeviceGuard guard(e->cfg.device);
     Staging &s = e->stage[0];
     const size_t bytes = (size_t)frames * sizeof(float);
+    if (e->h_in) {   // zero-copy (see aw_engine::h_in): one launch + one synchronisation per callback
+        const bool zdup = input_right == nullptr;
+        memcpy(e->h_in, input_left, bytes);
+        if (e->S == 2 && !zdup) memcpy(e->h_in + frames, input_right, bytes);
+        const int zrc = process_device_impl(e, StridedIn{e->h_in, (long long)e->S * frames, (long long)frames},
+                                            StridedOut{e->h_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, zdup && e->S == 2);
+        if (zrc != AW_OK) return zrc;
+        AW_CUDA(cudaStreamSynchronize(e->stream));
+        // left first, right second: with aliased outputs the right channel wins, as in RealtimeAudioProcessor.swift:181-182
+        memcpy(output_left, e->h_out, bytes);
+        memcpy(output_right, e->h_out + frames, bytes);
+        e->h2dBytes += bytes * ((e->S == 2 && !zdup) ? 2 : 1);
+        e->d2hBytes += 2 * bytes;
+        return AW_OK;
+    }
     AW_CUDA(cudaMemcpyAsync(s.d_in, input_left, bytes, cudaMemcpyHostToDevice, e->stream));
     const bool dup = input_right == nullptr;
     if (e->S == 2 && !dup) AW_CUDA(cudaMemcpyAsync(s.d_in + frames, input_right, bytes, cudaMemcpyHostToDevice, e->stream));
@@ -1280,6 +1400,30 @@ extern "C" int aw_engine_submit(aw_engine *e, const float *in, float *out, int f
     return AW_OK;
 }
 
+extern "C" int aw_engine_submit_device(aw_engine *e, const float *in, long long in_stream_stride, long long in_channel_stride, float *out,
+                                       int frames)
+{
+    if (!e || !in || !out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_engine_submit_device: null argument");
+    if (!(e->cfg.flags & AW_ENGINE_PIPELINED)) return set_error(AW_ERR_UNSUPPORTED, "engine was not created with AW_ENGINE_PIPELINED");
+    if (frames <= 0) return AW_OK;
+    if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");
+    DeviceGuard guard(e->cfg.device);
+    Staging &s = e->stage[e->nextStage];
+    e->nextStage ^= 1;
+    const size_t outBytes = (size_t)e->n * 2 * frames * sizeof(float);
+    if (s.busy) AW_CUDA(cudaStreamWaitEvent(e->stream, s.out_done, 0));   // this set's previous output has left the device
+    const int rc = process_device_impl(e, StridedIn{in, in_stream_stride, in_channel_stride},
+                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
+    if (rc != AW_OK) return rc;
+    AW_CUDA(cudaEventRecord(s.compute_done, e->stream));
+    AW_CUDA(cudaStreamWaitEvent(e->d2h, s.compute_done, 0));
+    AW_CUDA(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, e->d2h));
+    AW_CUDA(cudaEventRecord(s.out_done, e->d2h));
+    s.busy = true;
+    e->d2hBytes += outBytes;
+    return AW_OK;
+}
+
 extern "C" int aw_engine_wait(aw_engine *e)
 {
     if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
@@ -1307,6 +1451,7 @@ extern "C" int aw_engine_reset(aw_engine *e, int first, int count, int what)
         if (first == 0 && count == e->n) { e->pendingCount = 0; e->fifoReadIndex = 0; e->fifoCount = 0; }
         AW_CUDA(cudaStreamSynchronize(e->stream));
     }
+    if (first == 0 && count == e->n && (what & AW_RESET_SPATIAL) && (what & AW_RESET_EQ)) e->poisoned = false;
     if (what & AW_RESET_EQ) {
         split_machines(e, first);
         split_machines(e, first + count);
@@ -1332,7 +1477,7 @@ extern "C" int aw_engine_plan(const aw_engine *e, int *fused_tile, int *mac_tile
     if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
     if (fused_tile) *fused_tile = e->persistent ? e->persistentTile : e->fusedTile;
     if (mac_tile) *mac_tile = e->macTile;
-    if (partitions_cap) *partitions_cap = e->P_cap;
+    if (partitions_cap) *partitions_cap = e->P_cap > 0 ? e->P_cap - e->ringExtra : 0;
     return AW_OK;
 }
 

@@ -67,6 +67,18 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// evict_last for `pct` percent of the lines a copy touches (hardware picks which), evict_first for the rest: keeps a chosen
+// share of a streamed working set resident when all of it would not fit
+__device__ __forceinline__ uint64_t l2_policy_evict_last_share(int pct)
+{
+    uint64_t pol;
+    if (pct >= 88) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    else if (pct >= 63) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.75;" : "=l"(pol));
+    else if (pct >= 38) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.5;" : "=l"(pol));
+    else if (pct >= 13) asm volatile("createpolicy.fractional.L2::evict_last.L2::evict_first.b64 %0, 0.25;" : "=l"(pol));
+    else asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gsrc, unsigned bytes, uint64_t *bar, uint64_t policy)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
@@ -257,6 +269,7 @@ __device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fd
                                              bool active, int t, float *part_s, GroupBar gb = GroupBar{0, 0})
 {
     float sum = 0.f;
+    const int Pm = g.Pm > 0 ? g.Pm : g.P;
     if (active) {
         for (int s = 0; s < g.S; ++s) {
             const float *xrow = fdl_ny + ((size_t)stream * g.Se + s) * g.P_cap;
@@ -269,7 +282,7 @@ __device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fd
                     xa[k] = 0.f; ha[k] = 0.f;
                     if (p < g.P) {
                         int slot = g.head + p;
-                        if (slot >= g.P) slot -= g.P;
+                        if (slot >= Pm) slot -= Pm;
                         xa[k] = xrow[slot];
                         ha[k] = hrow[2 * p];
                     }

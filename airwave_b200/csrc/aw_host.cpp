@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -20,6 +21,7 @@ using namespace aw;
 // ---------------------------------------------------------------------------------------------
 static uint32_t rd32(const unsigned char *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 static uint16_t rd16(const unsigned char *p) { return (uint16_t)(p[0] | (p[1] << 8)); }
+static const long long kWavMaxFrames = 1ll << 28;   // frames fit an int; channels <= 65535 by the field width
 
 extern "C" int aw_wav_load_memory(const void *bytes, size_t size, aw_wav **out)
 {
@@ -55,11 +57,22 @@ extern "C" int aw_wav_load_memory(const void *bytes, size_t size, aw_wav **out)
     else if (tag == 1 && bits == 24) kind = I24;
     else if (tag == 1 && bits == 32) kind = I32;
     else return set_error(AW_ERR_WAV_UNSUPPORTED_FORMAT, "Unsupported WAV format");
-    aw_wav *w = new aw_wav();
+    // The header is untrusted (the reference gets this validation from AVAudioFile): a frame must hold all of its
+    // samples, or the reads below would run past the data chunk; and the planar copy must be allocatable.
+    if (block_align < channels * (bits / 8))
+        return set_error(AW_ERR_WAV_UNSUPPORTED_FORMAT, "Unsupported WAV format: block alignment smaller than channels x sample size");
+    if (frames > (size_t)kWavMaxFrames) return set_error(AW_ERR_WAV_UNSUPPORTED_FORMAT, "Unsupported WAV format: more than 2^28 frames");
+    aw_wav *w = nullptr;
+    try {
+        w = new aw_wav();
+        w->data.resize((size_t)channels * frames);
+    } catch (const std::bad_alloc &) {
+        delete w;
+        return set_error(AW_ERR_OUT_OF_MEMORY, "WAV file too large to load");
+    }
     w->sample_rate = (double)rate;
     w->channels = channels;
     w->frames = (int)frames;
-    w->data.resize((size_t)channels * frames);
     const int bps = bits / 8;
     for (size_t f = 0; f < frames; ++f) {
         for (int c = 0; c < channels; ++c) {
@@ -88,7 +101,12 @@ extern "C" int aw_wav_load(const char *path, aw_wav **out)
     std::vector<unsigned char> buf;
     unsigned char tmp[65536];
     size_t n;
-    while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    try {
+        while ((n = fread(tmp, 1, sizeof(tmp), f)) > 0) buf.insert(buf.end(), tmp, tmp + n);
+    } catch (const std::bad_alloc &) {
+        fclose(f);
+        return set_error(AW_ERR_OUT_OF_MEMORY, "WAV file too large to load");
+    }
     fclose(f);
     return aw_wav_load_memory(buf.data(), buf.size(), out);
 }

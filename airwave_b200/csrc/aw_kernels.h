@@ -14,6 +14,7 @@ struct BlockGeom {
     int B;              // block size = complex bins per spectrum
     int log2m;          // log2(B)
     int P;              // partitions of the segment's bank (ring modulus, ConvolutionEngine.swift:256-259)
+    int Pm;             // ring modulus when it differs from P (KP keeps one spare slot, see KpSegment); 0 = P
     int P_cap;          // FDL slots allocated per (stream, speaker)
     int head;           // fdlIndex after the decrement for this block
 };
@@ -102,17 +103,29 @@ struct EqFuse {             // equalizer fused into KP's epilogue (steady state 
 };
 bool persistent_can_fuse_eq(int log2m, int tile, int n_filters);
 int persistent_tiles(int log2m);                // bit mask of the tiles available for that transform size (0 = unsupported)
-struct KpSegment {          // a stream range bound to one bank (tile0 is filled in by the launcher)
+struct KpSegment {          // a stream range bound to one bank (tile0 and n_big are filled in by the launcher)
     int first_stream, n_streams;
-    int S, P, head;         // renderers, partitions (ring modulus), fdlIndex after this block's decrement
-    int tile0;
+    int S, P;               // renderers, partitions
+    int Pm;                 // ring modulus of the range's FDL rows: P + 1.  The reference's modulus is partitionCount
+                            // (ConvolutionEngine.swift:256-259); the spare slot lets the forward transform of block b+1 be
+                            // written while block b's multiply-accumulate still reads its P slots (one launch walks the k
+                            // blocks of a call).  Which slot holds which partition is internal state: outputs do not change.
+    int head;               // fdlIndex of the call's FIRST block, after its decrement; block b uses (head - b) mod Pm
+    int tile0, n_big;       // first tile of the range; its first n_big tiles hold T streams, the rest `small` streams
     const float4 *bank;
     const float *bank_ny;
 };
-constexpr int kKpMaxSegments = 64;   // per launch (64 x 40 B of the 4 KB kernel parameter space)
+constexpr int kKpMaxSegments = 64;   // per launch (64 x 48 B of the 4 KB kernel parameter space)
+struct KpCall {
+    int nb;                 // blocks of this call (frames = nb * B); input block b at cur + b*B, output block b at out + b*B
+    int order;              // walk order of the (tile, block) items of a CTA: 0 = block-major (all tiles of block 0, then block
+                            // 1, ...), 1 = tile-major (all blocks of a tile back to back: its FDL rows are re-read from L2)
+    int keep_pct;           // tile-major: percentage of the history rows loaded with L2 evict_last in all but the last block
+    int debug;              // timing experiments; ignored unless the library is built with -DAW_TIMING_EXPERIMENTS
+};
 cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_cap, int log2m, StridedIn cur, StridedIn prev,
                               float *overlap_save, float2 *fdl, float *fdl_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
-                              int debug, const EqFuse &eq, cudaStream_t st);
+                              const KpCall &call, const EqFuse &eq, cudaStream_t st);
 
 // Plan layout in global memory: M half-circle twiddles exp(-2*pi*i*k/(2M)) followed by plan_pt_entries(log2m) per-pass
 // twiddles (RegFft::pt_entry layout), M = 2^log2m complex points.

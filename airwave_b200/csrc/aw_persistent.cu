@@ -1,10 +1,12 @@
 // aw_persistent.cu — KP: the persistent warp-specialised block kernel (64 <= B <= 2048), the default hot path.
 //
-// One CTA per SM walks over tiles of T streams (T = 4 up to B = 512, 2 above).  For every tile it does what 2*S
-// ConvolutionEngine.process calls plus the RealtimeAudioProcessor mix do for T streams (ConvolutionEngine.swift:232-367,
-// RealtimeAudioProcessor.swift:146-163): forward real FFT of the T*S overlap-save frames, frequency-domain delay-line
-// multiply-accumulate over all (speaker, partition) pairs for both ears, inverse real FFT with the overlap-save discard.
-// One launch serves every stream range ("segment": streams bound to the same bank) of the engine; a tile looks its segment up.
+// One CTA per SM walks over work items (tile, block): a tile = up to T streams (T = 4 up to B = 512, 2 above), a block = one
+// of the nb B-frame blocks of the call (RealtimeAudioProcessor.swift:88-116 feeds processPendingBlock once per B frames; a call
+// of k*B frames is k blocks, rendered here by ONE launch).  For every item it does what 2*S ConvolutionEngine.process calls plus
+// the RealtimeAudioProcessor mix do for T streams (ConvolutionEngine.swift:232-367, RealtimeAudioProcessor.swift:146-163):
+// forward real FFT of the T*S overlap-save frames, frequency-domain delay-line multiply-accumulate over all (speaker,
+// partition) pairs for both ears, inverse real FFT with the overlap-save discard.  One launch serves every stream range
+// ("segment": streams bound to the same bank) of the engine; a tile looks its segment up.
 //
 //   producer warps      (4; 3 at B >= 512 with T = 4) one elected lane each; producer w fills the ring slots w, w+4, ...: FDL rows
 //                       and the matching filter rows go into a shared-memory ring with TMA-class bulk copies (cp.async.bulk ...
@@ -19,15 +21,20 @@
 //                       memory once per T streams (shared-memory bandwidth is the resource next to HBM here).  full/empty
 //                       mbarriers per ring slot.  The partial sums of the sets (and of the R rows side by side) are reduced
 //                       through shared memory in a fixed order (deterministic).
-//   FFT warps           (4, 8 or 12) run the forward transforms ONE TILE AHEAD of the MAC warps (nothing but the head slot of
-//                       the FDL depends on them), and the inverse transforms of the tile the MAC warps just finished
+//   FFT warps           (4, 8 or 12) run the forward transforms ONE ITEM AHEAD of the MAC warps (nothing but the head slot of
+//                       the FDL depends on them), and the inverse transforms of the item the MAC warps just finished
 //                       (accumulators handed over through shared memory, acc_ready/acc_free mbarriers).
 //
 // The head partition (p = 0) is streamed like any other row: the FFT warps publish it with a generic->async proxy fence
-// + a monotonic shared-memory count (release/acquire), which a producer checks before it issues a head row of a tile.
-// Stage order inside a tile (and column chunk): for every speaker its history partitions p = 1..P-1 in groups of RS, then
-// the S head rows — the same for every tile size and stream count, so a stream's output does not depend on how many
-// streams the engine renders or on which GPU it lives.
+// + a monotonic shared-memory count (release/acquire), which a producer checks before it issues a head row of an item.
+// The FDL ring of a (stream, speaker) has P + 1 slots: the forward transform of block b+1 (one item ahead) lands in the slot
+// block b does not read, so the k blocks of a call need no extra synchronisation — forward(i+2) is only issued after
+// inverse(i), i.e. after item i's multiply-accumulate has consumed all its rows.
+// Stage order inside an item (and column chunk) — B >= 256: for every speaker its history partitions p = 1..P-1 in groups of RS,
+// then the S head rows; B <= 128 (wide stages): for every speaker its partitions p = 0..P-1 in groups of RS — the same for every
+// tile size, stream count and blocks-per-call, so a stream's output does not depend on how many streams the engine renders, on
+// which GPU it lives, or on how a caller cuts its audio into calls (tested bit-exactly).
+// The last (partial) round of tiles is cut into tiles of T/2 or T/4 streams so that every SM gets a share of it.
 #include <stdlib.h>
 #include <string.h>
 
@@ -50,9 +57,10 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int RT = LOG2M <= 8 ? 2 : 1;            // rows per MAC thread
     static constexpr int RS = R * RT;                        // rows ((speaker, partition) pairs, consecutive partitions) per stage
     // Where does a speaker's head row (p = 0) go?  Wide stages (B <= 128: 8 or 4 rows) would waste a whole stage on it, so there it
-    // rides in the speaker's last history stage: rows are walked in ring-slot order head+1, ..., head+P-1, head (consecutive
-    // slots), i.e. partitions 1..P-1 then 0.  From B = 256 the heads are the last S stages of the tile, as late as possible, so
-    // that a launch's first tile never waits for its forward transforms.
+    // rides in the speaker's first stage: rows are walked in ring-slot order head, head+1, ..., head+P-1 (consecutive slots),
+    // i.e. partitions 0..P-1 (the forward transforms run a whole item ahead, so only a launch's very first stage waits for them).
+    // From B = 256 the heads are the last S stages of the item, as late as possible, so that a launch's first item never
+    // waits for its forward transforms.
     static constexpr bool MERGED = RS >= 4;
     // sets of 128 MAC threads; set q drains the ring slots q, q + MAC_SETS, ...  From B = 1024 the transforms, not the MAC, set the
     // pace (P is small, 10 transforms of 2B points per stream and block): one MAC set, and the threads go to the FFT warps.
@@ -87,26 +95,36 @@ template <int LOG2M, int T> struct PGeo {
     static_assert(NC == 1 || RS == 1, "column chunks carry one row per stage");
 };
 
-// One launch serves up to kMaxSegs stream ranges ("segments": streams bound to the same bank — per-device profiles,
+// Timing experiments (skip the transforms, their traffic or their arithmetic) exist only in builds made with
+// -DAW_TIMING_EXPERIMENTS; the shipped kernel cannot be told to skip work.
+#ifdef AW_TIMING_EXPERIMENTS
+#define AW_DBG(a) ((a).debug)
+#else
+#define AW_DBG(a) 0
+#endif
+
+// One launch serves up to kKpMaxSegments stream ranges ("segments": streams bound to the same bank — per-device profiles,
 // DeviceProfileManager.swift:4-12).  Tiles are numbered across the segments; a tile never straddles two of them.
 struct PersistArgs {
     int n_segs, n_tiles;
+    int small;                   // streams per tile behind a segment's first n_big tiles (T, T/2 or T/4)
+    int nb, order, keep_pct;     // KpCall
     int Se, P_cap;               // engine-wide layout of the state arrays (speakers per stream, FDL slots per (stream, speaker))
     KpSegment seg[kKpMaxSegments];
-    StridedIn cur, prev;
+    StridedIn cur, prev;         // block b of the call is cur + b*B; the block before block 0 is prev (inputOverlapBuffer)
     float *overlap_save;
     float2 *fdl;
     float *fdl_ny;
     StridedOut out;
     const float2 *tw;
-    int debug;   // timing experiments only: bit 0 skips the forward transforms, bit 1 the inverse transforms, bit 2 keeps the forward
-                 // transforms' arithmetic but not their memory traffic, bit 3 their traffic but not their arithmetic
-    EqFuse eq;   // steady-state equalizer applied to the block before it is stored (n_filters == 0: none)
+    int debug;   // AW_TIMING_EXPERIMENTS builds only: bit 0 skips the forward transforms, bit 1 the inverse transforms, bit 2 keeps the
+                 // forward transforms' arithmetic but not their memory traffic, bit 3 their traffic but not their arithmetic
+    EqFuse eq;   // steady-state equalizer applied to the block before it is stored (n_filters == 0: none); nb == 1 only
 };
 
 struct TileCtx {                 // what a role needs to know about the tile it works on
-    int s0, nvalid, last;        // first stream, valid streams (< T in a segment's last tile), last stream of the segment
-    int S, P, head, hs;          // renderers, partitions, FDL head slot, history stages per speaker
+    int s0, nvalid;              // first stream, valid streams (<= T)
+    int S, P, Pm, head, hs;      // renderers, partitions, ring modulus, FDL head slot of block 0, stages per speaker
     const float4 *bank;
     const float *bank_ny;
 };
@@ -118,10 +136,12 @@ __device__ __forceinline__ TileCtx tile_ctx(const PersistArgs &a, int tile)
     while (i + 1 < a.n_segs && tile >= a.seg[i + 1].tile0) ++i;
     const KpSegment &d = a.seg[i];
     TileCtx c;
-    c.s0 = d.first_stream + (tile - d.tile0) * T;
-    c.last = d.first_stream + d.n_streams - 1;
-    c.nvalid = min(T, c.last + 1 - c.s0);
-    c.S = d.S; c.P = d.P; c.head = d.head;
+    const int k = tile - d.tile0;
+    int size = T;
+    if (k < d.n_big) c.s0 = d.first_stream + k * T;
+    else { c.s0 = d.first_stream + d.n_big * T + (k - d.n_big) * a.small; size = a.small; }
+    c.nvalid = min(size, d.first_stream + d.n_streams - c.s0);
+    c.S = d.S; c.P = d.P; c.Pm = d.Pm; c.head = d.head;
     c.hs = MERGED ? (d.P + RS - 1) / RS : (d.P - 1 + RS - 1) / RS;   // stages per speaker (MERGED: head row included)
     c.bank = d.bank; c.bank_ny = d.bank_ny;
     return c;
@@ -146,12 +166,23 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     uint64_t *empty = full + STAGES;
     uint64_t *acc_ready = empty + STAGES;
     uint64_t *acc_free = acc_ready + 1;
-    unsigned *heads_done = reinterpret_cast<unsigned *>(acc_free + 1);   // FFT warps that have published their head rows, all tiles so far
+    unsigned *heads_done = reinterpret_cast<unsigned *>(acc_free + 1);   // FFT warps that have published their head rows, all items so far
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int nb = a.nb, n_items = my_tiles * nb;
+    const int dbg = AW_DBG(a);
     constexpr bool MERGED = PG::MERGED;
     auto my_tile = [&](int lt) { return tile_ctx<T, RS, MERGED>(a, (int)blockIdx.x + lt * (int)gridDim.x); };
+    // items of this CTA in walk order: (local tile lt, block b)
+    auto next_item = [&](int &lt, int &b) {
+        if (a.order) { if (++b == nb) { b = 0; ++lt; } }
+        else if (++lt == my_tiles) { lt = 0; ++b; }
+    };
+    auto head_of = [](const TileCtx &tc, int b) {                // fdlIndex of block b: it moves down one slot per block (:256-259)
+        int h = tc.head - (b < tc.Pm ? b : b % tc.Pm);
+        return h < 0 ? h + tc.Pm : h;
+    };
 
     for (int k = tid; k < PG::TW; k += PG::THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     if (tid == 0) {
@@ -162,7 +193,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    // Programmatic dependent launch: the next block's launch may be scheduled onto SMs as this grid's CTAs retire (its prologue
+    // Programmatic dependent launch: the next call's launch may be scheduled onto SMs as this grid's CTAs retire (its prologue
     // above touches nothing a previous launch writes), and this grid goes no further until the previous one has completed and
     // flushed — the FDL head slots, the overlap buffer and the output it wrote are read/overwritten below.
     asm volatile("griddepcontrol.launch_dependents;");
@@ -170,42 +201,55 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
 
     if (warp < PRODUCERS) {
         // ===== producers: warp w fills the ring slots w, w + PRODUCERS, ... every time the stage sequence comes round to them =====
-        if (lane == 0) {
+        if (lane == 0 && n_items > 0) {
             const size_t stream_stride = (size_t)a.Se * a.P_cap * halfB;
             const float4 *fdl4 = reinterpret_cast<const float4 *>(a.fdl);
-            // L2 priorities: history rows are read once per launch (evict first) — they must not push out the head rows the FFT
-            // warps have just written, nor the filter bank every tile re-reads (evict last)
+            // L2 priorities: history rows are read once per block (evict first) — they must not push out the head rows the FFT
+            // warps have just written, nor the filter bank every tile re-reads (evict last).  Tile-major calls re-read a tile's
+            // rows in its next block: there a share of them (keep_pct) is loaded evict_last in all but the call's last block.
             const uint64_t pol_stream = l2_policy_evict_first(), pol_keep = l2_policy_evict_last();
+            const uint64_t pol_reuse = l2_policy_evict_last_share(a.keep_pct);
             // position of this producer in the stage sequence, advanced one stage at a time (no divisions on the issue path):
-            // tile lt, column chunk c, and inside the chunk either history group jj of speaker s or the head row of speaker s
-            int lt = 0, c = 0, s = 0, jj = 0, stage = 0;
+            // item (lt, b), column chunk c, and inside the chunk either history group jj of speaker s or the head row of speaker s
+            int item = 0, lt = 0, b = 0, c = 0, s = 0, jj = 0, stage = 0;
             unsigned phase = 0;
             TileCtx tc = my_tile(0);
+            int hb = head_of(tc, 0);
             bool hist = MERGED || tc.hs > 0;
+            auto new_item = [&]() {
+                const int lt0 = lt;
+                ++item;
+                next_item(lt, b);
+                if (item < n_items) {
+                    if (lt != lt0) tc = my_tile(lt);
+                    hb = head_of(tc, b);
+                }
+            };
             auto advance = [&]() {
                 if (MERGED) {
                     if (++jj == tc.hs) {
                         jj = 0;
-                        if (++s == tc.S) { s = 0; if (++c == NC) { c = 0; ++lt; if (lt < my_tiles) tc = my_tile(lt); } }
+                        if (++s == tc.S) { s = 0; if (++c == NC) { c = 0; new_item(); } }
                     }
                 } else if (hist) {
                     if (++jj == tc.hs) { jj = 0; if (++s == tc.S) { s = 0; hist = false; } }
                 } else if (++s == tc.S) {
                     s = 0;
-                    if (++c == NC) { c = 0; ++lt; if (lt < my_tiles) tc = my_tile(lt); }
+                    if (++c == NC) { c = 0; new_item(); }
                     hist = tc.hs > 0;
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             };
-            for (int i = 0; i < warp; ++i) advance();        // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
-            while (lt < my_tiles) {
-                // rows of this stage: partitions p0, p0+1, ... (mod P: in the MERGED order the last one may be the head, p = 0)
-                const int p0 = MERGED ? 1 + jj * RS : (hist ? 1 + jj * RS : 0);
-                const int nrows = MERGED ? min(RS, tc.P - jj * RS) : (hist ? min(RS, tc.P - p0) : 1);
-                const bool has_head = MERGED ? (jj * RS + nrows == tc.P) : !hist;
-                // head rows of tile lt exist once every FFT warp has published them (a monotonic count: no phase to alias)
+            for (int i = 0; i < warp && item < n_items; ++i) advance();   // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
+            while (item < n_items) {
+                // rows of this stage: partitions p0, p0+1, ... in consecutive ring slots (MERGED: the first stage of a speaker starts
+                // with the head row, p = 0)
+                const int p0 = MERGED ? jj * RS : (hist ? 1 + jj * RS : 0);
+                const int nrows = MERGED ? min(RS, tc.P - p0) : (hist ? min(RS, tc.P - p0) : 1);
+                const bool has_head = MERGED ? (jj == 0) : !hist;
+                // head rows of an item exist once every FFT warp has published them (a monotonic count: no phase to alias)
                 if (has_head) {
-                    const unsigned need = (unsigned)(FFT_WARPS * (lt + 1));
+                    const unsigned need = (unsigned)(FFT_WARPS * (item + 1));
                     unsigned seen;
                     for (;;) {
                         asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(heads_done)) : "memory");
@@ -213,34 +257,31 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                         __nanosleep(128);
                     }
                 }
-                int slot = tc.head + p0;
-                if (slot >= tc.P) slot -= tc.P;              // modulus is partitionCount (Q4); p0 = P (a lone head row) lands on `head`
-                const int n1 = min(nrows, tc.P - slot);      // rows before the ring wraps
+                int slot = hb + p0;
+                if (slot >= tc.Pm) slot -= tc.Pm;            // the ring has Pm = P + 1 slots (Q4: the reference's has P)
+                const int n1 = min(nrows, tc.Pm - slot);     // rows before the ring wraps
                 mbar_wait(&empty[stage], phase ^ 1u);
-                mbar_expect_tx(&full[stage], (unsigned)(nrows * (T + 2) * C * sizeof(float4)));
+                mbar_expect_tx(&full[stage], (unsigned)(nrows * (tc.nvalid + 2) * C * sizeof(float4)));
                 float4 *dst = ring + (size_t)stage * stage_f4;
+                const uint64_t pol = has_head ? pol_keep : ((a.order && b + 1 < nb) ? pol_reuse : pol_stream);
 #pragma unroll
                 for (int u = 0; u < T; ++u) {
-                    const float4 *row = fdl4 + (size_t)min(tc.s0 + u, tc.last) * stream_stride + (size_t)s * a.P_cap * halfB + c * C;
-                    const uint64_t pol = has_head ? pol_keep : pol_stream;
-                    bulk_g2s_hint(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage], pol);
-                    if (RS > 1 && n1 < nrows)
-                        bulk_g2s_hint(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage], pol);
+                    if (u < tc.nvalid) {                     // a partial tile moves (and waits for) only the rows it has
+                        const float4 *row = fdl4 + (size_t)(tc.s0 + u) * stream_stride + (size_t)s * a.P_cap * halfB + c * C;
+                        bulk_g2s_hint(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage], pol);
+                        if (RS > 1 && n1 < nrows)
+                            bulk_g2s_hint(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage], pol);
+                    }
                 }
-                const float4 *frow = tc.bank + ((size_t)s * tc.P + (p0 < tc.P ? p0 : 0)) * M;
+                const float4 *frow = tc.bank + ((size_t)s * tc.P + p0) * M;
                 if (NC == 1) {                               // whole rows: both planes of RS consecutive partitions are contiguous
-                    // MERGED: the head's filter row (p = 0) is the first of the speaker's bank, not the one after p = P-1
-                    const int nf = (MERGED && has_head) ? nrows - 1 : nrows;
-                    if (nf > 0) bulk_g2s_hint(dst + T * RS * C, frow, (unsigned)(nf * 2 * C * sizeof(float4)), &full[stage], pol_keep);
-                    if (nf < nrows)
-                        bulk_g2s_hint(dst + T * RS * C + nf * 2 * C, tc.bank + (size_t)s * tc.P * M, (unsigned)(2 * C * sizeof(float4)),
-                                      &full[stage], pol_keep);
+                    bulk_g2s_hint(dst + T * RS * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage], pol_keep);
                 } else {
                     bulk_g2s_hint(dst + T * C, frow + c * C, (unsigned)(C * sizeof(float4)), &full[stage], pol_keep);
                     bulk_g2s_hint(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage], pol_keep);
                 }
                 const int step = stage + PRODUCERS < STAGES ? PRODUCERS : STAGES - stage + warp;   // to my next slot
-                for (int i = 0; i < step; ++i) advance();
+                for (int i = 0; i < step && item < n_items; ++i) advance();
             }
         }
     } else if (warp < PRODUCERS + MAC_WARPS) {
@@ -254,8 +295,9 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         unsigned phase = 0;
         int m = set;                                         // my next stage, relative to the current chunk
         constexpr int SETS = PG::MAC_SETS;
-        for (int lt = 0; lt < my_tiles; ++lt) {
-            const TileCtx tc = my_tile(lt);
+        int lt = 0, b = 0;
+        TileCtx tc = my_tiles > 0 ? my_tile(0) : TileCtx{};
+        for (int item = 0; item < n_items; ++item) {
             // first head stage of / stages per column chunk (MERGED: no separate head stages)
             const int hs = tc.hs, head0 = tc.S * hs, spc = MERGED ? head0 : head0 + tc.S;
             for (int c = 0; c < NC; ++c) {
@@ -297,8 +339,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     if (RS > 1 && hs > 0) { jj += SETS; while (jj >= hs) jj -= hs; }
                 }
                 m -= spc;                                    // position in the next chunk
-                // the FFT warps must be done with the previous tile's accumulators before they are overwritten
-                if (c == 0 && lt > 0) mbar_wait(acc_free, (unsigned)((lt - 1) & 1));
+                // the FFT warps must be done with the previous item's accumulators before they are overwritten
+                if (c == 0 && item > 0) mbar_wait(acc_free, (unsigned)((item - 1) & 1));
                 if constexpr (R == 1 && SETS == 1) {
 #pragma unroll
                     for (int v = 0; v < CW; ++v) {
@@ -381,60 +423,69 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_ready);
+            const int lt0 = lt;
+            next_item(lt, b);
+            if (item + 1 < n_items && lt != lt0) tc = my_tile(lt);
         }
     } else {
         // ===== FFT warps =====
         using F = RegFft<LOG2M>;
         const int ft = tid - 32 * PRODUCERS - PG::MAC_THREADS;
         const int f = ft / G, t = ft - f * G;
+        const int fwarp = ft >> 5;
         const int warp_first_f = G >= 32 ? f : (ft - lane) / G;   // first transform handled by this warp
         const GroupBar gb{BAR_FFT0 + f, G};
         float *my_part = part + (size_t)f * G;
 
-        auto forward_tile = [&](int lt) {
+        auto forward_item = [&](int lt, int b) {
             const TileCtx tc = my_tile(lt);
             const int s0 = tc.s0, nvalid = tc.nvalid;
             const int nfft = T * tc.S;
-            if (!(a.debug & 1)) {
+            const int hb = head_of(tc, b);
+            // overlap-save frame of block b = [block b-1 | block b] (:237-248); block -1 is the engine's inputOverlapBuffer
+            const StridedIn cur_b{a.cur.ptr + (size_t)b * M, a.cur.ss, a.cur.cs};
+            const StridedIn prev_b = b == 0 ? a.prev : StridedIn{a.cur.ptr + (size_t)(b - 1) * M, a.cur.ss, a.cur.cs};
+            float *ov_save = (b == nb - 1) ? a.overlap_save : nullptr;   // inputOverlapBuffer <- the call's last block (:243)
+            if (!(dbg & 1)) {
                 auto fetch = [&](int base, float2 (&v)[F::E], bool &active, int &stream, int &s) {
                     const int idx = base + f;
                     const int ls = idx / tc.S;
                     s = idx - ls * tc.S;
                     active = idx < nfft && ls < nvalid;
                     stream = s0 + (active ? ls : 0);
-                    const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
-                    const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
+                    const float *prev = prev_b.ptr + stream * prev_b.ss + s * prev_b.cs;
+                    const float *cur = cur_b.ptr + stream * cur_b.ss + s * cur_b.cs;
 #pragma unroll
                     for (int e = 0; e < F::E; ++e) {
                         const int i = F::template load_index<0>(t, e);   // frame = [previous block | current block] (:237-248)
-                        v[e] = (!active || (a.debug & (4 | 32))) ? make_float2(0.f, 0.f)
+                        v[e] = (!active || (dbg & (4 | 32))) ? make_float2(0.f, 0.f)
                                        : (i < M / 2 ? *reinterpret_cast<const float2 *>(prev + 2 * i) : *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2)));
                     }
                 };
                 auto transform = [&](float2 (&v)[F::E], bool active, int stream, int sp) {
-                    if (a.debug & 8) {                   // timing experiment: the forward transform's memory traffic without its arithmetic
+                    if (dbg & 8) {                       // timing experiment: the forward transform's memory traffic without its arithmetic
                         if (active) {
-                            float2 *dst = a.fdl + (((size_t)stream * a.Se + sp) * a.P_cap + tc.head) * M;
+                            float2 *dst = a.fdl + (((size_t)stream * a.Se + sp) * a.P_cap + hb) * M;
 #pragma unroll
                             for (int e = 0; e < F::E; ++e) {
                                 const int i = F::template load_index<0>(t, e);
                                 dst[i] = v[e];
-                                if (a.overlap_save && i >= M / 2) *reinterpret_cast<float2 *>(a.overlap_save + ((size_t)stream * a.Se + sp) * M + 2 * (i - M / 2)) = v[e];
+                                if (ov_save && i >= M / 2) *reinterpret_cast<float2 *>(ov_save + ((size_t)stream * a.Se + sp) * M + 2 * (i - M / 2)) = v[e];
                             }
                         }
                         return;
                     }
-                    if (a.debug & (4 | 16)) active = false;   // timing experiments: 4 = arithmetic without traffic, 16 = loads but no stores,
+                    if (dbg & (4 | 16)) active = false;       // timing experiments: 4 = arithmetic without traffic, 16 = loads but no stores,
                                                                 // 32 = stores but no loads
-                    if (active && a.overlap_save) {   // inputOverlapBuffer <- current block (:243); this thread read the same addresses as `prev`
-                        float *ov = a.overlap_save + ((size_t)stream * a.Se + sp) * M;
+                    if (active && ov_save) {
+                        float *ov = ov_save + ((size_t)stream * a.Se + sp) * M;
 #pragma unroll
                         for (int e = 0; e < F::E; ++e) {
                             const int i = F::template load_index<0>(t, e);
                             if (i >= M / 2) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v[e];
                         }
                     }
-                    const size_t row = ((size_t)stream * a.Se + sp) * a.P_cap + tc.head;
+                    const size_t row = ((size_t)stream * a.Se + sp) * a.P_cap + hb;
                     float2 *dst = a.fdl + row * M;
                     float *dst_ny = a.fdl_ny + row;
                     forward_frame_regs<LOG2M, true>(fftbuf + (size_t)f * PS, tw, t, active, v,
@@ -481,11 +532,35 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             epre = a.eq.prog->preamp_linear;
         }
 
-        auto inverse_tile = [&](int lt) {
+        auto inverse_item = [&](int lt, int b) {
             const TileCtx tc = my_tile(lt);
             const int s0 = tc.s0, nvalid = tc.nvalid;
             BlockGeom g;                                         // the Nyquist sum's view of this tile's segment
-            g.S = tc.S; g.Se = a.Se; g.P = tc.P; g.P_cap = a.P_cap; g.head = tc.head;
+            g.S = tc.S; g.Se = a.Se; g.P = tc.P; g.Pm = tc.Pm; g.P_cap = a.P_cap; g.head = head_of(tc, b);
+            if constexpr (G < 32) {
+                // narrow transforms: the Nyquist products of the tile's 2T outputs (S*P each) are summed by whole warps, outputs dealt
+                // round-robin to the FFT warps, and handed over through `part`
+                for (int idx = fwarp; idx < 2 * T; idx += FFT_WARPS) {
+                    const int ls = idx >> 1, ear = idx & 1;
+                    float sum = 0.f;
+                    if (ls < nvalid) {
+                        const float *xs = a.fdl_ny + (size_t)(s0 + ls) * a.Se * a.P_cap;
+                        const int n = tc.S * tc.P;
+                        int sp = 0, p = lane;                    // k = sp * P + p, k = lane, lane + 32, ...
+                        while (p >= tc.P) { p -= tc.P; ++sp; }
+                        for (int k = lane; k < n; k += 32) {
+                            int slot = g.head + p;
+                            if (slot >= tc.Pm) slot -= tc.Pm;
+                            sum = fmaf(xs[(size_t)sp * a.P_cap + slot], tc.bank_ny[(size_t)k * 2 + ear], sum);
+                            p += 32;
+                            while (p >= tc.P) { p -= tc.P; ++sp; }
+                        }
+                    }
+                    sum = group_sum(sum, 32);
+                    if (lane == 0) part[idx] = sum;
+                }
+                named_sync(BAR_EQ, PG::FFT_THREADS);
+            }
             for (int base = 0; base < 2 * T; base += NFT) {
                 if (base + warp_first_f >= 2 * T) continue;          // warp-uniform: no transform of this warp has work
                 const int idx = base + f;
@@ -494,18 +569,20 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 const int stream = s0 + (active ? ls : 0);
                 // idle transforms of a working warp run on their (free) forward buffer so the warp stays converged
                 float2 *buf = idx < 2 * T ? accbuf + (size_t)idx * PS : fftbuf + (size_t)f * PS;
-                const float ny = nyquist_sum<G>(g, a.fdl_ny, tc.bank_ny, stream, ear, active, t, my_part, gb);
+                float ny;
+                if constexpr (G < 32) ny = idx < 2 * T ? part[idx] : 0.f;
+                else ny = nyquist_sum<G>(g, a.fdl_ny, tc.bank_ny, stream, ear, active, t, my_part, gb);
                 if (gw == 0) {
-                    float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
+                    float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs + (size_t)b * M;
                     inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
                 } else {                                             // keep the block in shared memory (over the spectrum) for the EQ
                     float *eb = reinterpret_cast<float *>(buf);
                     inverse_frame<LOG2M, true, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { eb[2 * i] = x0; eb[2 * i + 1] = x1; }, gb);
                 }
             }
+            if constexpr (G < 32) named_sync(BAR_EQ, PG::FFT_THREADS);   // `part` may be rewritten by the next item
             if (gw > 0) {
                 named_sync(BAR_EQ, PG::FFT_THREADS);
-                const int fwarp = ft >> 5;
                 for (int ch0 = fwarp * eq_groups; ch0 < 2 * T; ch0 += FFT_WARPS * eq_groups) {   // warp-uniform
                     const int ch = ch0 + eg;
                     const bool live = eg < eq_groups && ch < 2 * T && (ch >> 1) < nvalid;
@@ -533,20 +610,23 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     const int ch = i / (M / 2), j = i - ch * (M / 2);
                     if ((ch >> 1) < nvalid) {
                         const float *eb = reinterpret_cast<const float *>(accbuf + (size_t)ch * PS);
-                        float *row = a.out.ptr + (size_t)(s0 + (ch >> 1)) * a.out.ss + (ch & 1) * a.out.cs;
+                        float *row = a.out.ptr + (size_t)(s0 + (ch >> 1)) * a.out.ss + (ch & 1) * a.out.cs + (size_t)b * M;
                         store_pair(a.out, row, 2 * j, eb[2 * j], eb[2 * j + 1]);
                     }
                 }
             }
         };
 
-        if (my_tiles > 0) forward_tile(0);
-        for (int lt = 0; lt < my_tiles; ++lt) {
-            if (lt + 1 < my_tiles) forward_tile(lt + 1);
-            mbar_wait_relaxed(acc_ready, (unsigned)(lt & 1));
-            if (!(a.debug & 2)) inverse_tile(lt);
+        int lt = 0, b = 0, ltn = 0, bn = 0;                      // item being finished, item being prepared
+        if (n_items > 0) forward_item(0, 0);
+        for (int item = 0; item < n_items; ++item) {
+            next_item(ltn, bn);
+            if (item + 1 < n_items) forward_item(ltn, bn);
+            mbar_wait_relaxed(acc_ready, (unsigned)(item & 1));
+            if (!(dbg & 2)) inverse_item(lt, b);
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);
+            lt = ltn; b = bn;
         }
     }
 }
@@ -598,25 +678,41 @@ int persistent_tiles(int log2m)
 
 cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_cap, int log2m, StridedIn cur, StridedIn prev,
                               float *overlap_save, float2 *fdl, float *fdl_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
-                              int debug, const EqFuse &eq, cudaStream_t st)
+                              const KpCall &call, const EqFuse &eq, cudaStream_t st)
 {
     if (n_segs <= 0) return cudaSuccess;
-    if (n_segs > kKpMaxSegments || !(persistent_tiles(log2m) & tile)) return cudaErrorInvalidValue;
+    if (n_segs > kKpMaxSegments || !(persistent_tiles(log2m) & tile) || call.nb < 1 || max_ctas < 1) return cudaErrorInvalidValue;
+    if (call.nb > 1 && (eq.n_filters != 0 || out.ring_cap > 0)) return cudaErrorInvalidValue;
     if (eq.n_filters != 0 && (n_segs != 1 || !persistent_can_fuse_eq(log2m, tile, eq.n_filters) || out.ring_cap > 0)) return cudaErrorInvalidValue;
     PersistArgs a;
     memset(&a, 0, sizeof(a));
-    int tiles = 0;
+    // Tiles of `tile` streams, numbered across the segments.  The last, partial round of tiles (big % ctas of them) would leave
+    // SMs idle while the others stream: it is cut into tiles of tile/2 or tile/4 streams, as many as still fit in one round.
+    int big = 0;
+    for (int i = 0; i < n_segs; ++i) big += (segs[i].n_streams + tile - 1) / tile;
+    if (big <= 0) return cudaSuccess;
+    const int rem = big % max_ctas;                        // tiles of the last round (all of them when there is only one)
+    int cut = 1;
+    if (eq.n_filters == 0)                                  // (the fused equalizer needs whole tiles per systolic round)
+        while (rem > 0 && cut * 2 <= tile && rem * cut * 2 <= max_ctas) cut *= 2;
+    const int small = tile / cut, keep = big - (cut > 1 ? rem : 0);   // the first `keep` tiles stay whole
+    int tiles = 0, seen = 0;
     for (int i = 0; i < n_segs; ++i) {
         a.seg[i] = segs[i];
+        const int nt = (segs[i].n_streams + tile - 1) / tile;
+        const int nbig = keep - seen < 0 ? 0 : (keep - seen < nt ? keep - seen : nt);
+        const int rest = segs[i].n_streams - nbig * tile;
         a.seg[i].tile0 = tiles;
-        tiles += (segs[i].n_streams + tile - 1) / tile;
+        a.seg[i].n_big = nbig;
+        tiles += nbig + (rest > 0 ? (rest + small - 1) / small : 0);
+        seen += nt;
     }
-    if (tiles <= 0) return cudaSuccess;
-    a.n_segs = n_segs; a.n_tiles = tiles; a.Se = Se; a.P_cap = P_cap;
+    a.n_segs = n_segs; a.n_tiles = tiles; a.small = small; a.Se = Se; a.P_cap = P_cap;
+    a.nb = call.nb; a.order = call.order ? 1 : 0; a.keep_pct = call.keep_pct;
     a.cur = cur; a.prev = prev; a.overlap_save = overlap_save; a.fdl = fdl; a.fdl_ny = fdl_ny; a.out = out; a.tw = tw;
-    a.debug = debug; a.eq = eq;
-    const int ctas = tiles < max_ctas ? tiles : max_ctas;
-#define AW_KP(L, TT) return launch_persistent_lt<L, TT>(a, ctas, st)
+    a.debug = call.debug; a.eq = eq;
+    const int grid = tiles < max_ctas ? tiles : max_ctas;
+#define AW_KP(L, TT) return launch_persistent_lt<L, TT>(a, grid, st)
     if (tile == 4) {
         switch (log2m) {
         case 6: AW_KP(6, 4);

@@ -350,16 +350,17 @@ def run_ours(args):
             eng.eq_prepare(defs[(r // 2) % 2], r * per, per if r < ranges - 1 else n - r * per)
     stream = torch.cuda.ExternalStream(eng.cuda_stream, device=local)
 
-    # device-resident synthetic input: a time-contiguous ring of R blocks per (stream, speaker)
-    R = 8
+    # device-resident synthetic input: a time-contiguous ring of R blocks per (stream, speaker); a step is one call of kb blocks
+    kb = max(1, min(args.blocks_per_call, e2e_frames // B))
+    R = max(8, 2 * kb)
     x = torch.empty((n, S, R * B), dtype=torch.float32, device=f"cuda:{local}")
-    y = torch.empty((n, 2, B), dtype=torch.float32, device=f"cuda:{local}")
+    y = torch.empty((n, 2, kb * B), dtype=torch.float32, device=f"cuda:{local}")
     aw._lib.check(aw.lib().aw_synth_fill_device(local, x.data_ptr(), rank * n, n, S, 0, R * B, SEED, None))
     torch.cuda.synchronize()
     xp, yp = x.data_ptr(), y.data_ptr()
 
     def step(j: int):
-        eng.process_device(xp + 4 * (j % R) * B, S * R * B, R * B, yp, 2 * B, B, B)
+        eng.process_device(xp + 4 * (j % (R // kb)) * kb * B, S * R * B, R * B, yp, 2 * kb * B, kb * B, kb * B)
 
     W = max(args.warmup, 3)
     sampler = ClockSampler(local)
@@ -411,7 +412,7 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     elapsed_ms_max = float(t.item())
-    value = world * n * K * (B / FS) / (elapsed_ms_max * 1e-3)
+    value = world * n * K * (kb * B / FS) / (elapsed_ms_max * 1e-3)
 
     # per-kernel pass (same steps, events around every launch) -> roofline of the dominant kernel
     prof_steps = min(K, 200)
@@ -421,13 +422,13 @@ def run_ours(args):
     prof = eng.profile_end()
     peak, peak_src = measured_peaks()
     plan = eng.plan()
-    step_bytes = n * algorithmic_bytes(S, B, P, eq_filters)
+    step_bytes = kb * n * algorithmic_bytes(S, B, P, eq_filters)
     step_ms = elapsed_ms_max / K
     kernels_ms = {k: v["ms"] / max(v["launches"], 1) for k, v in prof.items()}
     if len(plan["kernels"]) == 1:
         # one kernel does the whole block (K2+K3+K4): its algorithmic bytes are SURVEY.md 8(d)'s per-stream figure x streams
         dom_name = plan["kernels"][0]
-        dom_ms, dom_bytes = kernels_ms[dom_name], n * algorithmic_bytes(S, B, P)
+        dom_ms, dom_bytes = kernels_ms[dom_name], kb * n * algorithmic_bytes(S, B, P)
         if eq_filters == 0 and len(banks) == 1:
             # the timed region is K launches of this one kernel and nothing else: its average launch duration is at most the step
             # time (the per-launch events of the profiling pass add a few microseconds of their own)
@@ -484,7 +485,7 @@ def run_ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "streams_per_gpu": n, "speakers": S, "block": B, "partitions": P,
-                       "taps": taps, "step": f"one {B}-frame block for all streams (forward FFT -> FDL multiply-accumulate -> inverse FFT"
+                       "taps": taps, "blocks_per_step": kb, "step": f"{kb} x {B}-frame block(s) for all streams, one call (forward FFT -> FDL multiply-accumulate -> inverse FFT"
                                + (f" -> {eq_filters}-biquad float64 EQ cascade)" if eq_filters else ")"),
                        "l2": f"inputs larger than L2: the FDL working set read every step is {n * 8 * S * B * P / 1e6:.0f} MB (L2 = 126 MB)",
                        "plan": plan},
@@ -520,6 +521,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
+    ap.add_argument("--blocks-per-call", type=int, default=1, help="blocks per device-resident call of the timed region (a step)")
     ap.add_argument("--e2e-frames", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

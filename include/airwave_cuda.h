@@ -208,6 +208,12 @@ AW_API int aw_engine_process_device(aw_engine *engine, const float *in, long lon
 /* Pipelined host path for offline batch rendering: copies and kernels of consecutive submits overlap;
  * `out` is valid after aw_engine_wait().  in/out must stay alive (and should be pinned) until then. */
 AW_API int aw_engine_submit(aw_engine *engine, const float *in, float *out, int frames);
+/* Same pipeline with the input already resident on the DEVICE (strides in elements): offline batch rendering whose input is
+ * produced or decoded on the GPU — BASELINE.json configs[4] (16,384 streams x 60 s: 188.7 GB of input per GPU would not cross
+ * the host link).  `in` may be rewritten once work submitted later on aw_engine_stream() runs; `out`
+ * (HOST) is valid after aw_engine_wait().  No reference counterpart: the reference renders one stream on the CPU. */
+AW_API int aw_engine_submit_device(aw_engine *engine, const float *in, long long in_stream_stride, long long in_channel_stride,
+                                   float *out, int frames);
 AW_API int aw_engine_wait(aw_engine *engine);
 /* Single-stream mirror of StereoAudioProcessing.process (AudioPipeline.swift:3-11) for an engine with n_streams == 1
  * and n_speakers <= 2: input_right may be NULL (mono duplicated), output_left may alias output_right. HOST pointers. */

@@ -146,6 +146,24 @@ def test_wav_sample_formats_and_errors():
             aw.WAVLoader.load(bad)
         assert e.value.status == status
 
+def test_wav_loader_rejects_hostile_headers():
+    """The header is untrusted: block_align smaller than a frame's samples would make the loader read past the data chunk
+    (the reference gets this check from AVAudioFile); such files are refused, never read out of bounds."""
+    def hostile(tag, bits, channels, block_align, payload):
+        fmt = struct.pack("<HHIIHH", tag, channels, 48000, 48000 * block_align, block_align, bits)
+        body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"data" + struct.pack("<I", len(payload)) + payload
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+    for tag, bits, ch, ba in [(3, 32, 14, 1), (3, 64, 4096, 2), (1, 16, 2, 3), (1, 24, 65535, 1)]:
+        with pytest.raises(aw.AirwaveError) as e:
+            aw.WAVLoader.load(hostile(tag, bits, ch, ba, b"\x00" * 64))
+        assert e.value.status == 33, (tag, bits, ch, ba)
+    # padding inside a frame (block_align larger than the samples) is legal and decodes like the tight layout
+    tight = np.array([[0.25, -0.5], [0.125, 1.0]], "<f4")
+    padded = b"".join(row.tobytes() + b"\xff" * 4 for row in tight)
+    w = aw.WAVLoader.load(hostile(3, 32, 2, 12, padded))
+    assert np.array_equal(w.audioData, tight.T)
+
+
 
 def test_layouts_and_hesuvi_maps():
     assert aw.InputLayout.surround71().channels == oracle.InputLayout.surround71.channels

@@ -182,6 +182,9 @@ PATHS = [  # (name, env, block sizes it exists for)
     ("persistent T=2", {"AW_PERSISTENT_TILE": "2"}, (64, 128, 256, 512, 1024, 2048)),
     ("persistent T=2, 3 CTAs", {"AW_PERSISTENT_CTAS": "3", "AW_PERSISTENT_TILE": "2"}, (64, 128, 256, 512, 1024, 2048)),
     ("persistent T=4, 2 CTAs", {"AW_PERSISTENT_CTAS": "2", "AW_PERSISTENT_TILE": "4"}, (64, 128, 256, 512)),
+    ("persistent, one launch per block", {"AW_KP_MULTIBLOCK": "0"}, (64, 128, 256, 512, 1024, 2048)),
+    ("persistent, block-major", {"AW_KP_ORDER": "0", "AW_PERSISTENT_CTAS": "2"}, (64, 128, 256, 512, 1024, 2048)),
+    ("persistent, tile-major, 2 CTAs", {"AW_KP_ORDER": "1", "AW_PERSISTENT_CTAS": "2", "AW_KP_KEEP": "100"}, (64, 128, 256, 512, 1024, 2048)),
     ("fused", {"AW_PERSISTENT": "0"}, (64, 128, 256, 512)),
     ("split", {"AW_FUSED_TILE": "0"}, (64, 128, 256, 512, 1024, 2048)),
 ]
@@ -218,8 +221,39 @@ def test_execution_paths_agree(aw, hrtf_path, block):
     for few in ("persistent T=2, 3 CTAs", "persistent T=4, 2 CTAs"):   # every CTA walks several tiles
         if few in results:
             assert np.array_equal(results[few][0], base), few
+    # a call of k blocks is one launch that walks (tile, block) items: neither one launch per block nor the walk order
+    # (block-major / tile-major) may change a bit
+    for variant in ("persistent, one launch per block", "persistent, block-major", "persistent, tile-major, 2 CTAs"):
+        assert np.array_equal(results[variant][0], base), variant
     for name, (y, _) in results.items():
         assert np.abs(y - base).max() <= 4e-6, name
+
+
+@pytest.mark.parametrize("block,n", [(64, 700), (256, 1201), (512, 37), (1024, 301)])
+def test_blocks_per_call_do_not_change_a_bit(aw, hrtf_path, block, n):
+    """RealtimeAudioProcessor.process cuts a callback into B-frame blocks (RealtimeAudioProcessor.swift:88-116): how a caller
+    cuts its audio into calls must not change the samples.  Calls of 1, 3 and 16 blocks (one KP launch each, the ring slots of a
+    (stream, speaker) written and read across block boundaries inside the launch) against one block per call, with enough
+    streams that every CTA walks several tiles and the last round is cut into partial tiles."""
+    lay = aw.InputLayout.surround71()
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), FS, lay, block)
+    blocks = 48 if block <= 256 else 12
+    unique = 5
+    base = None
+    for k, env in [(1, None), (3, None), (16, None), (4, {"AW_KP_ORDER": "0"}), (4, {"AW_PERSISTENT_TILE": "2", "AW_KP_KEEP": "0"})]:
+        if k * block > 4096:
+            k = 4096 // block
+        xu, y, plan = _render_twins(aw, bank, n, 8, block, blocks=blocks, unique=unique, per_call=k * block, pcm_lr=None, env=env)
+        assert plan["kernels"][0].startswith("k_persistent<"), plan
+        for i in range(unique, n):
+            assert np.array_equal(y[i], y[i % unique]), (k, i)
+        if base is None:
+            base = y[:unique].copy()
+            h = oracle.hrir_matrix(oracle.load_wav(hrtf_path("RoomSH1.0")), FS, oracle.InputLayout.surround71)
+            ref = oracle.direct_conv_f64(xu[0], h)
+            assert np.abs(base[0] - ref).max() <= MAX_ABS and snr_db(ref, base[0]) >= SNR_DB
+        else:
+            assert np.array_equal(y[:unique], base), (k, env)
 
 
 def test_small_and_ragged_stream_counts_and_stereo_on_the_persistent_path(aw, hrtf_path):
