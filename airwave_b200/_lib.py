@@ -45,6 +45,7 @@ ERR_EQ_INVALID_SAMPLE_RATE, ERR_EQ_NON_FINITE_PREAMP, ERR_EQ_TOO_MANY_FILTERS, E
 ERR_WAV_READ, ERR_WAV_CHANNEL_COUNT, ERR_WAV_EMPTY, ERR_WAV_UNSUPPORTED_FORMAT, ERR_EQ_PARSE = 30, 31, 32, 33, 40
 ENGINE_LITERAL_STEREO, ENGINE_PIPELINED = 1, 2
 RESET_SPATIAL, RESET_EQ = 1, 2
+RESAMPLE_REFERENCE, RESAMPLE_CORRECT = 0, 1
 LAYOUT_STEREO, LAYOUT_SURROUND51, LAYOUT_SURROUND71, LAYOUT_ATMOS714 = 2, 6, 8, 12
 FILTER_TYPES = {"peaking": 0, "lowShelf": 1, "highShelf": 2, "PK": 0, "LSC": 1, "HSC": 2, 0: 0, 1: 1, 2: 2}
 FILTER_NAMES = {0: "peaking", 1: "lowShelf", 2: "highShelf"}
@@ -87,7 +88,9 @@ def lib() -> C.CDLL:
     L.aw_hesuvi_parse.argtypes = [C.c_char_p, ip, ip]
     L.aw_resample_output_count.argtypes = [C.c_int, C.c_double, C.c_double]
     L.aw_resample.argtypes = [C.c_int, fp, C.c_int, C.c_double, C.c_double, fp, C.c_int, ip]
+    L.aw_resample_ex.argtypes = [C.c_int, fp, C.c_int, C.c_double, C.c_double, C.c_int, fp, C.c_int, ip]
     L.aw_bank_create.argtypes = [C.c_int, fp, C.c_int, C.c_int, C.c_double, C.c_double, ip, ip, C.c_int, C.c_int, C.POINTER(vp)]
+    L.aw_bank_create_ex.argtypes = [C.c_int, fp, C.c_int, C.c_int, C.c_double, C.c_double, ip, ip, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.aw_bank_create_from_wav.argtypes = [C.c_int, vp, C.c_double, C.c_int, C.c_int, C.POINTER(vp)]
     L.aw_bank_info.argtypes = [vp, ip, ip, ip, ip]
     L.aw_bank_read.argtypes = [vp, fp, fp]

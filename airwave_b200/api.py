@@ -168,16 +168,21 @@ class HRIRChannelMap:
 
 
 class Resampler:
-    """Resampler.resampleHighQuality (Resampler.swift:31-68), computed on the device."""
+    """Resampler.resampleHighQuality (Resampler.swift:31-68), computed on the device.
+
+    ``correct=False`` (default) reproduces the reference literally, including its time compression of up-sampled responses
+     and the refusal of down-sampling; ``correct=True`` is the flagged alternative: time-correct linear
+    interpolation in float64, down-sampling allowed."""
 
     @staticmethod
-    def resampleHighQuality(input, fromRate: float, toRate: float, device: int = 0) -> np.ndarray:
+    def resampleHighQuality(input, fromRate: float, toRate: float, device: int = 0, correct: bool = False) -> np.ndarray:
         x = _f32(input)
         n = L.lib().aw_resample_output_count(len(x), fromRate, toRate)
         out = np.zeros(max(n, len(x), 1), np.float32)
         written = C.c_int()
-        L.check(L.lib().aw_resample(device, x.ctypes.data_as(C.POINTER(C.c_float)), len(x), fromRate, toRate,
-                                    out.ctypes.data_as(C.POINTER(C.c_float)), len(out), C.byref(written)))
+        L.check(L.lib().aw_resample_ex(device, x.ctypes.data_as(C.POINTER(C.c_float)), len(x), fromRate, toRate,
+                                       L.RESAMPLE_CORRECT if correct else L.RESAMPLE_REFERENCE,
+                                       out.ctypes.data_as(C.POINTER(C.c_float)), len(out), C.byref(written)))
         return out[: written.value]
 
 
@@ -186,13 +191,14 @@ class HRIRBank:
     """Frequency-domain HRIR filter bank resident in HBM (aw_bank): what HRIRManager.activatePreset's
     build loop + ConvolutionEngine.init produce, once per (preset, rate, block) instead of per engine."""
 
-    def __init__(self, pcm, src_rate: float, dst_rate: float, left_idx, right_idx, block: int, device: int = 0):
+    def __init__(self, pcm, src_rate: float, dst_rate: float, left_idx, right_idx, block: int, device: int = 0,
+                 correct_resampling: bool = False):
         pcm = _f32(pcm)
         assert pcm.ndim == 2
         h = C.c_void_p()
-        L.check(L.lib().aw_bank_create(device, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.shape[0], pcm.shape[1],
-                                       src_rate, dst_rate, _iarr(list(left_idx)), _iarr(list(right_idx)), len(left_idx),
-                                       block, C.byref(h)))
+        L.check(L.lib().aw_bank_create_ex(device, pcm.ctypes.data_as(C.POINTER(C.c_float)), pcm.shape[0], pcm.shape[1],
+                                          src_rate, dst_rate, _iarr(list(left_idx)), _iarr(list(right_idx)), len(left_idx),
+                                          block, L.RESAMPLE_CORRECT if correct_resampling else L.RESAMPLE_REFERENCE, C.byref(h)))
         self._h, self.device = h, device
         self._read_info()
 

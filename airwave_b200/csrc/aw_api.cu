@@ -324,6 +324,9 @@ int eq_prepare_state(aw_engine *e, double preampDB, const aw_eq_filter *filters,
     return AW_OK;
 }
 
+// BEGIN REALTIME PATH — everything from here to the END marker runs inside aw_engine_process*: no allocation, no container growth,
+// no locks, no logging, no device-wide synchronisation (the analogue of scripts/check-audio-safety-invariants.sh:23-41 is
+// tests/test_abi.py::test_realtime_path_gate, which greps this region).  Error paths (set_error) may build a message.
 // ---- render-thread half of ParametricEqualizerProcessor (:317-407), one instance per EqMachine --------
 int eq_begin_transition(aw_engine *e, EqMachine &m, int target)   // :354-359
 {
@@ -715,6 +718,8 @@ int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, 
     return AW_OK;
 }
 
+// END REALTIME PATH
+
 void free_engine(aw_engine *e)
 {
     if (!e) return;
@@ -841,10 +846,13 @@ extern "C" int aw_resample_output_count(int count, double from_rate, double to_r
     return (int)((double)count / stride);                        // :39
 }
 
-extern "C" int aw_resample(int device, const float *input, int count, double from_rate, double to_rate, float *output, int capacity,
-                           int *written)
+extern "C" int aw_resample_ex(int device, const float *input, int count, double from_rate, double to_rate, int mode, float *output,
+                              int capacity, int *written)
 {
     if (!input || !output || count <= 0) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_resample: bad argument");
+    if (mode != AW_RESAMPLE_REFERENCE && mode != AW_RESAMPLE_CORRECT) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_resample: unknown mode");
+    if (!(from_rate > 0) || !(to_rate > 0) || !std::isfinite(from_rate) || !std::isfinite(to_rate))
+        return set_error(AW_ERR_INVALID_ARGUMENT, "aw_resample: sample rates must be finite and positive");
     const int outCount = aw_resample_output_count(count, from_rate, to_rate);
     if (written) *written = outCount > 0 ? outCount : 0;
     if (std::fabs(from_rate - to_rate) < 0.01) {
@@ -853,7 +861,8 @@ extern "C" int aw_resample(int device, const float *input, int count, double fro
         return AW_OK;
     }
     if (outCount <= 0) return AW_OK;                             // :41
-    if (outCount < count) return set_error(AW_ERR_RESAMPLE_DOWN, "down-sampling reads past the control vector in the reference");
+    if (mode == AW_RESAMPLE_REFERENCE && outCount < count)
+        return set_error(AW_ERR_RESAMPLE_DOWN, "down-sampling reads past the control vector in the reference");
     if (capacity < outCount) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_resample: capacity too small");
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(AW_ERR_CUDA, "cudaSetDevice failed");
@@ -861,7 +870,9 @@ extern "C" int aw_resample(int device, const float *input, int count, double fro
     AW_CUDA(cudaMalloc(&d_in, sizeof(float) * count));
     cudaError_t e = cudaMalloc(&d_out, sizeof(float) * outCount);
     if (e == cudaSuccess) e = cudaMemcpy(d_in, input, sizeof(float) * count, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_resample_vgenp(d_in, 1, count, (float)(from_rate / to_rate), d_out, outCount, 0);
+    if (e == cudaSuccess)
+        e = mode == AW_RESAMPLE_CORRECT ? launch_resample_linear(d_in, 1, count, from_rate / to_rate, d_out, outCount, 0)
+                                        : launch_resample_vgenp(d_in, 1, count, (float)(from_rate / to_rate), d_out, outCount, 0);
     if (e == cudaSuccess) e = cudaMemcpy(output, d_out, sizeof(float) * outCount, cudaMemcpyDeviceToHost);
     cudaFree(d_in);
     cudaFree(d_out);
@@ -869,15 +880,30 @@ extern "C" int aw_resample(int device, const float *input, int count, double fro
     return AW_OK;
 }
 
+extern "C" int aw_resample(int device, const float *input, int count, double from_rate, double to_rate, float *output, int capacity,
+                           int *written)
+{
+    return aw_resample_ex(device, input, count, from_rate, to_rate, AW_RESAMPLE_REFERENCE, output, capacity, written);
+}
+
 // ---- bank -------------------------------------------------------------------------------------------------
 extern "C" int aw_bank_create(int device, const float *pcm, int channels, int frames, double src_rate, double dst_rate,
                               const int *left_idx, const int *right_idx, int n_speakers, int block, aw_bank **out)
+{
+    return aw_bank_create_ex(device, pcm, channels, frames, src_rate, dst_rate, left_idx, right_idx, n_speakers, block,
+                             AW_RESAMPLE_REFERENCE, out);
+}
+
+extern "C" int aw_bank_create_ex(int device, const float *pcm, int channels, int frames, double src_rate, double dst_rate,
+                                 const int *left_idx, const int *right_idx, int n_speakers, int block, int resample_mode, aw_bank **out)
 {
     if (!out) return set_error(AW_ERR_INVALID_ARGUMENT, "aw_bank_create: null out");
     *out = nullptr;
     if (!pcm || !left_idx || !right_idx || channels <= 0 || frames <= 0 || n_speakers <= 0)
         return set_error(AW_ERR_INVALID_ARGUMENT, "aw_bank_create: bad argument");
     if (!is_pow2(block) || block < 4 || block > 8192) return set_error(AW_ERR_INVALID_BLOCK_SIZE, "ConvolutionEngine: block size must be a power of two in [4, 8192]");
+    if (resample_mode != AW_RESAMPLE_REFERENCE && resample_mode != AW_RESAMPLE_CORRECT)
+        return set_error(AW_ERR_INVALID_ARGUMENT, "aw_bank_create: unknown resampling mode");
     // build loop of HRIRManager.activatePreset (:366-418): skip unmapped speakers, validate indices
     std::vector<int> l, r;
     for (int i = 0; i < n_speakers; ++i) {
@@ -895,7 +921,8 @@ extern "C" int aw_bank_create(int device, const float *pcm, int channels, int fr
     if (resample) {
         taps = aw_resample_output_count(frames, src_rate, dst_rate);
         if (taps <= 0) return set_error(AW_ERR_INVALID_ARGUMENT, "resampled impulse response is empty");
-        if (taps < frames) return set_error(AW_ERR_RESAMPLE_DOWN, "down-sampling reads past the control vector in the reference");
+        if (taps < frames && resample_mode == AW_RESAMPLE_REFERENCE)
+            return set_error(AW_ERR_RESAMPLE_DOWN, "down-sampling reads past the control vector in the reference");
     }
     DeviceGuard guard(device);
     if (!guard.ok) return set_error(AW_ERR_CUDA, "cudaSetDevice failed (no CUDA device? there is no CPU fallback)");
@@ -917,7 +944,9 @@ extern "C" int aw_bank_create(int device, const float *pcm, int channels, int fr
     const float *d_src = d_ir;
     if (e == cudaSuccess && resample) {
         e = cudaMalloc(&d_rs, sizeof(float) * (size_t)S * 2 * taps);
-        if (e == cudaSuccess) e = launch_resample_vgenp(d_ir, S * 2, frames, (float)(src_rate / dst_rate), d_rs, taps, 0);
+        if (e == cudaSuccess)
+            e = resample_mode == AW_RESAMPLE_CORRECT ? launch_resample_linear(d_ir, S * 2, frames, src_rate / dst_rate, d_rs, taps, 0)
+                                                     : launch_resample_vgenp(d_ir, S * 2, frames, (float)(src_rate / dst_rate), d_rs, taps, 0);
         d_src = d_rs;
     }
     if (e == cudaSuccess) e = cudaMalloc(&b->d_bank, sizeof(float4) * (size_t)S * b->P * block);
@@ -1290,6 +1319,7 @@ extern "C" int aw_engine_eq_hold_publication(aw_engine *e, int first, int count,
     return AW_OK;
 }
 
+// BEGIN REALTIME PATH — the process entry points
 extern "C" int aw_engine_process_device(aw_engine *e, const float *in, long long in_stream_stride, long long in_channel_stride,
                                         float *out, long long out_stream_stride, long long out_channel_stride, int frames)
 {
@@ -1433,6 +1463,8 @@ extern "C" int aw_engine_wait(aw_engine *e)
     AW_CUDA(cudaStreamSynchronize(e->d2h));
     return AW_OK;
 }
+
+// END REALTIME PATH
 
 extern "C" int aw_engine_reset(aw_engine *e, int first, int count, int what)
 {

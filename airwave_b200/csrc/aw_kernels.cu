@@ -61,6 +61,35 @@ cudaError_t launch_resample_vgenp(const float *in, int rows, int count, float st
     return cudaGetLastError();
 }
 
+// K6b  AW_RESAMPLE_CORRECT: what Resampler.swift:16-30 documents ("linear interpolation ... at the target rate") rather than
+// what its vgenp call computes.  Source position n * fromRate / toRate in float64, explicit round-to-nearest operations so
+// that the numpy float64 restatement in oracle/binding.py (resample_linear_f64) matches bit for bit.
+__global__ void k_resample_linear(const float *__restrict__ in, int rows, int count, double step, float *__restrict__ out, int out_count)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    const int row = blockIdx.y;
+    if (n >= out_count || row >= rows) return;
+    const float *x = in + (size_t)row * count;
+    const double pos = __dmul_rn((double)n, step);
+    float r;
+    if (pos >= (double)(count - 1)) r = x[count - 1];          // past the last sample: hold it
+    else {
+        const int m = (int)pos;                                  // pos >= 0: truncation = floor
+        const double frac = __dsub_rn(pos, (double)m);
+        const double a = (double)x[m], d = __dsub_rn((double)x[m + 1], a);
+        r = (float)__dadd_rn(a, __dmul_rn(d, frac));
+    }
+    out[(size_t)row * out_count + n] = r;
+}
+
+cudaError_t launch_resample_linear(const float *in, int rows, int count, double step, float *out, int out_count, cudaStream_t st)
+{
+    if (rows <= 0 || out_count <= 0) return cudaSuccess;
+    dim3 grid((out_count + 255) / 256, rows);
+    k_resample_linear<<<grid, 256, 0, st>>>(in, rows, count, step, out, out_count);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // K7  frame adapter
 // ------------------------------------------------------------------------------------------------

@@ -44,6 +44,8 @@ cudaError_t launch_bank_build(const float *ir, int S, int taps, int B, int log2m
                               const float2 *tw, cudaStream_t st);
 // K6: Resampler.resampleHighQuality (vDSP_vramp + vDSP_vgenp semantics), rows x count -> rows x out_count
 cudaError_t launch_resample_vgenp(const float *in, int rows, int count, float step, float *out, int out_count, cudaStream_t st);
+// K6b: time-correct linear interpolation (AW_RESAMPLE_CORRECT): out[n] = lerp(in, n * step), float64 position and blend
+cudaError_t launch_resample_linear(const float *in, int rows, int count, double step, float *out, int out_count, cudaStream_t st);
 // K7: frame adapter pieces (RealtimeAudioProcessor.swift:88-116, 166-171, 174-190)
 cudaError_t launch_gather_pending(StridedIn in, int in_offset, int copy_count, float *pending, int pending_count, int n_streams,
                                   int S, int B, int dup_mono, cudaStream_t st);

@@ -166,7 +166,10 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     uint64_t *empty = full + STAGES;
     uint64_t *acc_ready = empty + STAGES;
     uint64_t *acc_free = acc_ready + 1;
-    unsigned *heads_done = reinterpret_cast<unsigned *>(acc_free + 1);   // FFT warps that have published their head rows, all items so far
+    // FFT warps that have published their head rows, counted separately for even and odd items: a warp without work in an item
+    // runs ahead of the others — by at most one item (it waits for acc_ready before the next forward pass), so with two
+    // counters its early arrival for item i+1 cannot be mistaken for another warp's arrival for item i
+    unsigned *heads_done = reinterpret_cast<unsigned *>(acc_free + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -187,7 +190,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
     for (int k = tid; k < PG::TW; k += PG::THREADS) tw[k] = RegFft<LOG2M>::pt_entry(a.tw, k);
     if (tid == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], SET_WARPS); }
-        *heads_done = 0;
+        heads_done[0] = 0;
+        heads_done[1] = 0;
         mbar_init(acc_ready, MAC_WARPS);
         mbar_init(acc_free, FFT_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             // position of this producer in the stage sequence, advanced one stage at a time (no divisions on the issue path):
             // item (lt, b), column chunk c, and inside the chunk either history group jj of speaker s or the head row of speaker s
             int item = 0, lt = 0, b = 0, c = 0, s = 0, jj = 0, stage = 0;
-            unsigned phase = 0;
+            unsigned phase = 0, seen0 = 0, seen1 = 0;        // last values read from heads_done[0], [1]
             TileCtx tc = my_tile(0);
             int hb = head_of(tc, 0);
             bool hist = MERGED || tc.hs > 0;
@@ -247,15 +251,22 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 const int p0 = MERGED ? jj * RS : (hist ? 1 + jj * RS : 0);
                 const int nrows = MERGED ? min(RS, tc.P - p0) : (hist ? min(RS, tc.P - p0) : 1);
                 const bool has_head = MERGED ? (jj == 0) : !hist;
-                // head rows of an item exist once every FFT warp has published them (a monotonic count: no phase to alias)
-                if (has_head) {
-                    const unsigned need = (unsigned)(FFT_WARPS * (item + 1));
-                    unsigned seen;
+                // Head rows of an item exist once every FFT warp has published them (a monotonic count: no phase to alias).  The
+                // history rows of block b > 0 include the head rows this launch wrote for blocks < b of the same tile: the newest
+                // of them belongs to the tile's previous item — and this producer may be a whole ring ahead of the producer
+                // that waited for it, so it checks for itself.
+                const int dep = has_head ? item : (b > 0 ? (a.order ? item - 1 : item - my_tiles) : -1);
+                const unsigned need = dep < 0 ? 0u : (unsigned)(FFT_WARPS * ((dep >> 1) + 1));
+                if (dep >= 0 && ((dep & 1) ? seen1 : seen0) < need) {
+                    unsigned got;
                     for (;;) {
-                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(seen) : "r"(smem_u32(heads_done)) : "memory");
-                        if (seen >= need) break;
+                        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(got) : "r"(smem_u32(heads_done + (dep & 1))) : "memory");
+                        if (got >= need) break;
                         __nanosleep(128);
                     }
+                    if (dep & 1) seen1 = got; else seen0 = got;
+                    // the acquire above is a generic-proxy operation; the bulk copies below read through the async proxy: order them
+                    asm volatile("fence.proxy.async;" ::: "memory");
                 }
                 int slot = hb + p0;
                 if (slot >= tc.Pm) slot -= tc.Pm;            // the ring has Pm = P + 1 slots (Q4: the reference's has P)
@@ -435,9 +446,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         const int fwarp = ft >> 5;
         const int warp_first_f = G >= 32 ? f : (ft - lane) / G;   // first transform handled by this warp
         const GroupBar gb{BAR_FFT0 + f, G};
-        float *my_part = part + (size_t)f * G;
 
-        auto forward_item = [&](int lt, int b) {
+        auto forward_item = [&](int lt, int b, int item) {
             const TileCtx tc = my_tile(lt);
             const int s0 = tc.s0, nvalid = tc.nvalid;
             const int nfft = T * tc.S;
@@ -517,7 +527,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             __threadfence();
             asm volatile("fence.proxy.async;" ::: "memory");
             __syncwarp();
-            if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(heads_done)) : "memory");
+            if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(heads_done + (item & 1))) : "memory");
         };
 
         // fused equalizer (ParametricEqualizerState.process, ParametricEqualizerProcessor.swift:58-91): a systolic array across the
@@ -532,35 +542,35 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             epre = a.eq.prog->preamp_linear;
         }
 
-        auto inverse_item = [&](int lt, int b) {
+        auto inverse_item = [&](int lt, int b, int item) {
             const TileCtx tc = my_tile(lt);
             const int s0 = tc.s0, nvalid = tc.nvalid;
             BlockGeom g;                                         // the Nyquist sum's view of this tile's segment
             g.S = tc.S; g.Se = a.Se; g.P = tc.P; g.Pm = tc.Pm; g.P_cap = a.P_cap; g.head = head_of(tc, b);
-            if constexpr (G < 32) {
-                // narrow transforms: the Nyquist products of the tile's 2T outputs (S*P each) are summed by whole warps, outputs dealt
-                // round-robin to the FFT warps, and handed over through `part`
-                for (int idx = fwarp; idx < 2 * T; idx += FFT_WARPS) {
-                    const int ls = idx >> 1, ear = idx & 1;
-                    float sum = 0.f;
-                    if (ls < nvalid) {
-                        const float *xs = a.fdl_ny + (size_t)(s0 + ls) * a.Se * a.P_cap;
-                        const int n = tc.S * tc.P;
-                        int sp = 0, p = lane;                    // k = sp * P + p, k = lane, lane + 32, ...
+            // The Nyquist products of the item's 2T outputs (S*P each) are summed by whole warps, outputs dealt round-robin to the FFT
+            // warps, and handed over through `part` (double-buffered by item parity).  The barrier also orders every read of
+            // the Nyquist side array before the forward transforms two items ahead, which overwrite this block's oldest slot.
+            float *ny_part = part + (item & 1) * 2 * T;
+            for (int idx = fwarp; idx < 2 * T; idx += FFT_WARPS) {
+                const int ls = idx >> 1, ear = idx & 1;
+                float sum = 0.f;
+                if (ls < nvalid) {
+                    const float *xs = a.fdl_ny + (size_t)(s0 + ls) * a.Se * a.P_cap;
+                    const int n = tc.S * tc.P;
+                    int sp = 0, p = lane;                        // k = sp * P + p, k = lane, lane + 32, ...
+                    while (p >= tc.P) { p -= tc.P; ++sp; }
+                    for (int k = lane; k < n; k += 32) {
+                        int slot = g.head + p;
+                        if (slot >= tc.Pm) slot -= tc.Pm;
+                        sum = fmaf(xs[(size_t)sp * a.P_cap + slot], tc.bank_ny[(size_t)k * 2 + ear], sum);
+                        p += 32;
                         while (p >= tc.P) { p -= tc.P; ++sp; }
-                        for (int k = lane; k < n; k += 32) {
-                            int slot = g.head + p;
-                            if (slot >= tc.Pm) slot -= tc.Pm;
-                            sum = fmaf(xs[(size_t)sp * a.P_cap + slot], tc.bank_ny[(size_t)k * 2 + ear], sum);
-                            p += 32;
-                            while (p >= tc.P) { p -= tc.P; ++sp; }
-                        }
                     }
-                    sum = group_sum(sum, 32);
-                    if (lane == 0) part[idx] = sum;
                 }
-                named_sync(BAR_EQ, PG::FFT_THREADS);
+                sum = group_sum(sum, 32);
+                if (lane == 0) ny_part[idx] = sum;
             }
+            named_sync(BAR_EQ, PG::FFT_THREADS);
             for (int base = 0; base < 2 * T; base += NFT) {
                 if (base + warp_first_f >= 2 * T) continue;          // warp-uniform: no transform of this warp has work
                 const int idx = base + f;
@@ -569,9 +579,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 const int stream = s0 + (active ? ls : 0);
                 // idle transforms of a working warp run on their (free) forward buffer so the warp stays converged
                 float2 *buf = idx < 2 * T ? accbuf + (size_t)idx * PS : fftbuf + (size_t)f * PS;
-                float ny;
-                if constexpr (G < 32) ny = idx < 2 * T ? part[idx] : 0.f;
-                else ny = nyquist_sum<G>(g, a.fdl_ny, tc.bank_ny, stream, ear, active, t, my_part, gb);
+                const float ny = idx < 2 * T ? ny_part[idx] : 0.f;
                 if (gw == 0) {
                     float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs + (size_t)b * M;
                     inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
@@ -580,7 +588,6 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                     inverse_frame<LOG2M, true, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { eb[2 * i] = x0; eb[2 * i + 1] = x1; }, gb);
                 }
             }
-            if constexpr (G < 32) named_sync(BAR_EQ, PG::FFT_THREADS);   // `part` may be rewritten by the next item
             if (gw > 0) {
                 named_sync(BAR_EQ, PG::FFT_THREADS);
                 for (int ch0 = fwarp * eq_groups; ch0 < 2 * T; ch0 += FFT_WARPS * eq_groups) {   // warp-uniform
@@ -618,12 +625,12 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         };
 
         int lt = 0, b = 0, ltn = 0, bn = 0;                      // item being finished, item being prepared
-        if (n_items > 0) forward_item(0, 0);
+        if (n_items > 0) forward_item(0, 0, 0);
         for (int item = 0; item < n_items; ++item) {
             next_item(ltn, bn);
-            if (item + 1 < n_items) forward_item(ltn, bn);
+            if (item + 1 < n_items) forward_item(ltn, bn, item + 1);
             mbar_wait_relaxed(acc_ready, (unsigned)(item & 1));
-            if (!(dbg & 2)) inverse_item(lt, b);
+            if (!(dbg & 2)) inverse_item(lt, b, item);
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);
             lt = ltn; b = bn;

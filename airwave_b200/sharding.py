@@ -32,9 +32,24 @@ def owner_of(stream: int, n_streams: int, world_size: int) -> int:
     return r
 
 
+def _comm_device(group=None):
+    """Where tensors must live for a collective of this group: NCCL only moves device memory, gloo moves host memory."""
+    import torch
+    import torch.distributed as dist
+
+    if dist.get_backend(group) == "nccl":
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device("cpu")
+
+
+def _equal_counts(n: int, world: int) -> bool:
+    return len({stream_shard(n, world, r)[1] for r in range(world)}) == 1
+
+
 def gather_outputs(local_out: np.ndarray, n_streams: int, group=None) -> Optional[np.ndarray]:
     """Host gather of per-rank output blocks [count_r][2][frames] into [n_streams][2][frames] on rank 0
-    (the reference-side consumer is a host; nothing here touches the render path)."""
+    (the reference-side consumer is a host; nothing here touches the render path).  Under NCCL the blocks travel
+    through device memory (NCCL rejects host tensors) and are copied back on rank 0."""
     import torch
     import torch.distributed as dist
 
@@ -42,36 +57,57 @@ def gather_outputs(local_out: np.ndarray, n_streams: int, group=None) -> Optiona
     first, count = stream_shard(n_streams, world, rank)
     assert local_out.shape[0] == count
     frames = local_out.shape[2]
-    parts = [torch.empty((stream_shard(n_streams, world, r)[1], 2, frames), dtype=torch.float32) for r in range(world)]
-    dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(local_out, np.float32)), group=group) if _equal_counts(n_streams, world) \
-        else _gather_uneven(parts, local_out, group)
+    dev = _comm_device(group)
+    mine = torch.from_numpy(np.ascontiguousarray(local_out, np.float32)).to(dev)
+    parts = [torch.empty((stream_shard(n_streams, world, r)[1], 2, frames), dtype=torch.float32, device=dev) for r in range(world)]
+    if _equal_counts(n_streams, world):
+        dist.all_gather(parts, mine, group=group)
+    else:
+        for r in range(world):
+            if r == rank:
+                parts[r].copy_(mine)
+            dist.broadcast(parts[r], src=r, group=group)
     if rank != 0:
         return None
-    return torch.cat(parts, 0).numpy()
+    return torch.cat(parts, 0).cpu().numpy()
 
 
-def _equal_counts(n: int, world: int) -> bool:
-    return len({stream_shard(n, world, r)[1] for r in range(world)}) == 1
+def sample_streams(n_streams: int, world_size: int, per_rank: int = 4) -> list:
+    """Global stream ids used to prove the sharding contract: for every rank the first and last streams of its
+    shard and a few in between — the ones a single-GPU engine re-renders for the bit-exact comparison."""
+    ids = []
+    for r in range(world_size):
+        first, count = stream_shard(n_streams, world_size, r)
+        if count <= 0:
+            continue
+        k = min(per_rank, count)
+        ids.extend(sorted({first + (i * (count - 1)) // max(k - 1, 1) for i in range(k)}))
+    return ids
 
 
-def _gather_uneven(parts, local_out, group) -> None:
+def gather_samples(local_out: np.ndarray, n_streams: int, ids, group=None) -> Optional[np.ndarray]:
+    """Gathers the rows of the sampled global stream ids from their owners: [len(ids)][2][frames] on rank 0, else None.
+    local_out holds this rank's shard [count][2][frames]."""
     import torch
     import torch.distributed as dist
 
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    mine = torch.from_numpy(np.ascontiguousarray(local_out, np.float32))
-    for r in range(world):
-        if r == rank:
-            parts[r].copy_(mine)
-        dist.broadcast(parts[r], src=r, group=group)
+    first, count = stream_shard(n_streams, world, rank)
+    frames = local_out.shape[2]
+    dev = _comm_device(group)
+    rows = torch.zeros((len(ids), 2, frames), dtype=torch.float32, device=dev)
+    for i, g in enumerate(ids):
+        if first <= g < first + count:
+            rows[i] = torch.from_numpy(np.ascontiguousarray(local_out[g - first], np.float32)).to(dev)
+    # every row has exactly one owner and is zero elsewhere: a sum moves it without changing a value
+    dist.reduce(rows, dst=0, op=dist.ReduceOp.SUM, group=group)
+    return rows.cpu().numpy() if rank == 0 else None
 
 
 def max_over_ranks(value: float, group=None) -> float:
     import torch
     import torch.distributed as dist
 
-    t = torch.tensor([value], dtype=torch.float64)
-    if dist.get_backend(group) == "nccl":
-        t = t.cuda()
+    t = torch.tensor([value], dtype=torch.float64, device=_comm_device(group))
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())

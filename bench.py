@@ -53,6 +53,11 @@ WORKLOADS = {
     "C5-1024": ("7.1->binaural, RoomSH1.0, B=1024, 2048 streams/GPU", 8, 1024, 2048, "RoomSH1.0"),
     "C5-2048": ("7.1->binaural, RoomSH1.0, B=2048, 2048 streams/GPU", 8, 2048, 2048, "RoomSH1.0"),
     "C5-4096": ("7.1->binaural, RoomSH1.0, B=4096, 2048 streams/GPU", 8, 4096, 2048, "RoomSH1.0"),
+    # BASELINE.json configs[4] as specified: offline batch render, 2,048 streams per GPU x 60 s, block-size sweep; input synthesised
+    # on the device chunk by chunk (188.7 GB per GPU would not cross the host link), output copied to
+    # pinned host memory through aw_engine_submit_device / aw_engine_wait.  The block size in this tuple is the headline entry.
+    "C5-offline": ("offline batch render, 7.1->binaural, RoomSH1.0, 2048 streams/GPU x 60 s, block sweep 64..4096, device-synthesised "
+                   "input, output to pinned host memory", 8, 256, 2048, "RoomSH1.0"),
 }
 
 
@@ -298,23 +303,240 @@ def hesuvi14_cpu(S: int):
     return [m.getIndices(s)[0] for s in lay.channels], [m.getIndices(s)[1] for s in lay.channels]
 
 
-def run_ours(args):
-    import numpy as np
-    import torch
-    import airwave_b200 as aw
+def percentile(sorted_values, q):
+    return sorted_values[min(len(sorted_values) - 1, int(q * len(sorted_values)))]
 
+
+def init_ranks(torch):
+    """(rank, world, local, dist-or-None) from the torchrun environment; one process per GPU, NCCL for control only."""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available() or aw.device_count() < 1:
-        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
-    affinity = pin_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def shard_check(aw, torch, dist, rank, world, local, n, S, B, bank_args, frames):
+    """Hardware proof of the sharding contract: rank r renders global streams [r*n, (r+1)*n) on GPU r; a
+    single-GPU engine on rank 0 re-renders a sample of the same global ids; the outputs must be bit-identical."""
+    import numpy as np
+    from airwave_b200 import sharding
+    bank = aw.HRIRBank(*bank_args, device=local)
+    eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=frames, max_partitions=bank.partitions, device=local)
+    eng.set_bank(bank)
+    x = torch.empty((n, S, frames), dtype=torch.float32, device=f"cuda:{local}")
+    y = torch.empty((n, 2, frames), dtype=torch.float32, device=f"cuda:{local}")
+    aw._lib.check(aw.lib().aw_synth_fill_device(local, x.data_ptr(), rank * n, n, S, 0, frames, SEED, None))
+    torch.cuda.synchronize()
+    eng.process_device(x.data_ptr(), S * frames, frames, y.data_ptr(), 2 * frames, frames, frames)
+    torch.cuda.synchronize()
+    mine = y.cpu().numpy()
+    eng.close()
+    total = world * n
+    ids = sharding.sample_streams(total, world, per_rank=4)
+    checks = torch.tensor([float(mine.astype("float64").sum())], dtype=torch.float64, device=f"cuda:{local}")
+    all_checks = [torch.zeros_like(checks) for _ in range(world)]
+    if dist is not None:
+        rows = sharding.gather_samples(mine, total, ids)
+        dist.all_gather(all_checks, checks)
+    else:
+        rows, all_checks = mine[ids], [checks]
+    result = None
+    if rank == 0:
+        ref = aw.BinauralEngine(len(ids), S, B, FS, max_frames_per_call=frames, max_partitions=bank.partitions, device=local)
+        ref.set_bank(bank)
+        xr = torch.empty((len(ids), S, frames), dtype=torch.float32, device=f"cuda:{local}")
+        yr = torch.empty((len(ids), 2, frames), dtype=torch.float32, device=f"cuda:{local}")
+        for i, g in enumerate(ids):          # stream g's signal depends on its GLOBAL id only
+            aw._lib.check(aw.lib().aw_synth_fill_device(local, xr[i].data_ptr(), g, 1, S, 0, frames, SEED, None))
+        torch.cuda.synchronize()
+        ref.process_device(xr.data_ptr(), S * frames, frames, yr.data_ptr(), 2 * frames, frames, frames)
+        torch.cuda.synchronize()
+        want = yr.cpu().numpy()
+        ref.close()
+        result = {"global_streams": total, "sampled_ids": ids, "frames": frames,
+                  "bit_identical_to_single_gpu": bool(np.array_equal(rows, want)) and bool(np.abs(want).max() > 0),
+                  "per_rank_checksum": [float(c.item()) for c in all_checks]}
+    return result
+
+
+def run_sync_latency(aw, local):
+    """The reference's real-time contract is synchronous: process(inputLeft:...frameCount:) returns filled buffers
+    (AudioPipeline.swift:3-11), one 512-frame block per callback = 10.7 ms of audio (HRIRManager.swift:149).  Host->host latency
+    of aw_engine_process_stereo (C1) and aw_engine_process (n streams of 7.1, B = 256), with and without zero-copy staging."""
+    import ctypes as C
+    import numpy as np
+    out = {}
+    lib = aw.lib()
+    wav = aw.WAVLoader.load(os.path.join(GOLDEN, "hrtf", "NeutralSH1.0.wav"))
+
+    def timed(call, reps):
+        for _ in range(200):
+            call()
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter_ns()
+            call()
+            t.append((time.perf_counter_ns() - t0) * 1e-3)
+        t.sort()
+        return {"p50_us": round(percentile(t, 0.5), 2), "p99_us": round(percentile(t, 0.99), 2), "mean_us": round(sum(t) / len(t), 2), "calls": reps}
+
+    for mode in ("zero_copy", "staged_copies"):
+        os.environ["AW_ZERO_COPY"] = "1" if mode == "zero_copy" else "0"
+        res = {}
+        bank = aw.HRIRBank.from_wav(wav, FS, aw.InputLayout.stereo(), 512, device=local)
+        for frames in (512, 2048):
+            eng = aw.BinauralEngine(1, 2, 512, FS, max_frames_per_call=4096, max_partitions=bank.partitions, device=local, literal_stereo=True)
+            eng.set_bank(bank)
+            l = (np.random.default_rng(1).random(frames, dtype=np.float32) - 0.5) * 0.5
+            r = (np.random.default_rng(2).random(frames, dtype=np.float32) - 0.5) * 0.5
+            ol, orr = np.zeros(frames, np.float32), np.zeros(frames, np.float32)
+            args = (eng._h, l.ctypes.data_as(C.c_void_p), r.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p),
+                    orr.ctypes.data_as(C.c_void_p), frames)
+            res[f"process_stereo_{frames}_frames"] = timed(lambda: lib.aw_engine_process_stereo(*args), 10000 if frames == 512 else 3000)
+            eng.close()
+        wav71 = aw.WAVLoader.load(os.path.join(GOLDEN, "hrtf", "RoomSH1.0.wav"))
+        bank71 = aw.HRIRBank.from_wav(wav71, FS, aw.InputLayout.surround71(), 256, device=local)
+        for n in (1, 16, 64):
+            eng = aw.BinauralEngine(n, 8, 256, FS, max_frames_per_call=256, max_partitions=bank71.partitions, device=local)
+            eng.set_bank(bank71)
+            x = ((np.random.default_rng(3).random((n, 8, 256), dtype=np.float32) - 0.5) * 0.5)
+            y = np.zeros((n, 2, 256), np.float32)
+            args = (eng._h, x.ctypes.data_as(C.c_void_p), y.ctypes.data_as(C.c_void_p), 256)
+            res[f"process_{n}_streams_7.1_256_frames"] = timed(lambda: lib.aw_engine_process(*args), 3000)
+            eng.close()
+        out[mode] = res
+    os.environ.pop("AW_ZERO_COPY", None)
+    p50 = out["zero_copy"]["process_stereo_512_frames"]["p50_us"]
+    out["callback_period_us"] = 512 / FS * 1e6
+    out["headroom_vs_10.7ms_callback"] = round(512 / FS * 1e6 / p50, 1)
+    out["how"] = ("time.perf_counter_ns around the ctypes call (host pointers in ordinary pageable memory, result in the caller's buffer on "
+                  "return); zero_copy = kernels read/write page-locked mapped staging directly, staged_copies = cudaMemcpyAsync both ways")
+    return out
+
+
+def run_offline(args):
+    """BASELINE.json configs[4]: offline batch render of 2,048 streams per GPU x `--offline-seconds` s, one pass per block size."""
+    import numpy as np
+    import torch
+    import airwave_b200 as aw
+    from airwave_b200 import sharding
+
+    if not torch.cuda.is_available() or aw.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    rank, world, local, dist = init_ranks(torch)
+    affinity = pin_to_gpu_numa_node(local) if world > 1 else None
+    desc, S, B_head, n, hrir = WORKLOADS[args.workload]
+    if args.streams > 0:
+        n = args.streams
+    pcm, rate = hrir_pcm(hrir)
+    l_idx, r_idx = speaker_maps(S)
+    blocks = [int(b) for b in args.offline_blocks.split(",")]
+    seconds = args.offline_seconds
+    F = 4096                                           # frames per call (chunk): the adapter's maximum (RealtimeAudioProcessor.swift:85)
+    chunks = max(2, int(round(seconds * FS / F)))
+    rendered_s = chunks * F / FS
+    x = torch.empty((n, S, F), dtype=torch.float32, device=f"cuda:{local}")
+    hout = [aw.PinnedBuffer((n, 2, F)) for _ in range(2)]
+    sampler = ClockSampler(local)
+    sampler.start()
+    t_all0 = time.time()
+    sweep = []
+    launches = 0
+    for B in blocks:
+        bank = aw.HRIRBank(pcm, rate, FS, l_idx, r_idx, B, device=local)
+        eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=F, max_partitions=bank.partitions, device=local, pipelined=True)
+        eng.set_bank(bank)
+        st = eng.cuda_stream
+        xp = x.data_ptr()
+
+        def chunk(c):
+            aw._lib.check(aw.lib().aw_synth_fill_device(local, xp, rank * n, n, S, c * F, F, SEED, st))
+            eng.submit_device(xp, S * F, F, hout[c % 2].array.ctypes.data, F)
+
+        for c in range(3):                             # warm-up: fills the FDL (P*B <= 4352 frames) and the pipeline
+            chunk(c)
+        eng.wait()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        c0 = eng.counters()
+        t0 = time.perf_counter()
+        for c in range(chunks):
+            chunk(3 + c)
+        eng.wait()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        c1 = eng.counters()
+        launches += int(c1["kernel_launches"] - c0["kernel_launches"])
+        checksum = float(hout[(3 + chunks - 1) % 2].array[:, :, -1].astype("float64").sum())
+        dt_max = sharding.max_over_ranks(dt) if dist is not None else dt
+        # device time per call (events around 40 calls, nothing else on the stream)
+        stream = torch.cuda.ExternalStream(st, device=local)
+        y = torch.empty((n, 2, F), dtype=torch.float32, device=f"cuda:{local}")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(41)]
+        ev[0].record(stream)
+        for j in range(40):
+            eng.process_device(xp, S * F, F, y.data_ptr(), 2 * F, F, F)
+            ev[j + 1].record(stream)
+        torch.cuda.synchronize()
+        per_call = sorted(ev[j].elapsed_time(ev[j + 1]) for j in range(40))
+        nb = F // B
+        peak, _ = measured_peaks()
+        dev_ms = per_call[len(per_call) // 2]
+        entry = {"block": B, "partitions": bank.partitions, "block_period_ms": 1e3 * B / FS,
+                 "e2e_value": world * n * rendered_s / dt_max, "elapsed_s": dt_max, "rendered_s_per_stream": rendered_s,
+                 "device_ms_per_call": {"p50": dev_ms, "p99": percentile(per_call, 0.99)},
+                 "device_ms_per_block": {"p50": dev_ms / nb, "p99": percentile(per_call, 0.99) / nb},
+                 "device_value_per_gpu": n * (F / FS) / (dev_ms * 1e-3),
+                 "roofline_frac": nb * n * algorithmic_bytes(S, B, bank.partitions) / (dev_ms * 1e-3) / 1e9 / peak,
+                 "d2h_gbs_per_gpu": n * 2 * F * 4 * chunks / dt_max / 1e9, "kernels": eng.plan()["kernels"], "checksum_rank0": checksum}
+        sweep.append(entry)
+        eng.close()
+        del bank
+    t_all1 = time.time()
+    clocks = sampler.stop(t_all0, t_all1)
+    if rank == 0:
+        head = next((e for e in sweep if e["block"] == B_head), sweep[0])
+        peak, peak_src = measured_peaks()
+        line = {
+            "metric": METRIC, "value": head["device_value_per_gpu"] * world, "unit": UNIT, "n_gpus": world, "steps": 40, "warmup": 3,
+            "ms_per_step": head["device_ms_per_call"]["p50"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (generated on the device, counter-based, keyed by global stream id)",
+            "config": {"workload": f"{args.workload}: {desc}", "streams_per_gpu": n, "speakers": S, "headline_block": head["block"],
+                       "seconds_per_stream": rendered_s, "frames_per_call": F,
+                       "step": f"one {F}-frame call ({F // head['block']} blocks, one launch) for all streams + its output copied to the host",
+                       "l2": "inputs larger than L2: FDL working set 571 MB+ per GPU"},
+            "e2e": {"value": head["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": n * 2 * F * 4,
+                    "timing": "host wall clock around the render loop (device synth -> aw_engine_submit_device -> pinned host), "
+                              "synchronised on both sides, max over ranks"},
+            "roofline": {"bound": "hbm", "kernel": head["kernels"][0], "achieved": head["roofline_frac"] * peak, "peak": peak, "unit": "GB/s",
+                         "frac": head["roofline_frac"], "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes of SURVEY.md 8(d) per block; a 4096-frame call re-reads a tile's FDL rows from L2, "
+                                 "so the fraction may exceed what one block per launch can reach"},
+            "sweep": sweep, "gpu_launches": launches, "host_affinity": affinity, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import airwave_b200 as aw
+
+    if not torch.cuda.is_available() or aw.device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    rank, world, local, dist = init_ranks(torch)
+    affinity = pin_to_gpu_numa_node(local) if world > 1 else None
 
     desc, S, B, n, hrir = WORKLOADS[args.workload]
     if args.streams > 0:
@@ -408,10 +630,8 @@ def run_ours(args):
         events[j + 1].record(stream)
     torch.cuda.synchronize()
     per_step = sorted(events[j].elapsed_time(events[j + 1]) for j in range(KL))
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=f"cuda:{local}")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms_max = float(t.item())
+    from airwave_b200 import sharding
+    elapsed_ms_max = sharding.max_over_ranks(elapsed_ms) if dist is not None else elapsed_ms
     value = world * n * K * (kb * B / FS) / (elapsed_ms_max * 1e-3)
 
     # per-kernel pass (same steps, events around every launch) -> roofline of the dominant kernel
@@ -464,10 +684,57 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     checksum = float(hout[(e2e_steps - 1) % n_bufs].array[:, :, -1].astype("float64").sum())
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    e2e_s_max = sharding.max_over_ranks(e2e_s) if dist is not None else e2e_s
+    e2e_value = world * n * e2e_steps * (F / FS) / e2e_s_max
+    e2e_checks = [checksum]
     if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps * (F / FS) / float(te.item())
+        tc = torch.tensor([checksum], dtype=torch.float64, device=f"cuda:{local}")
+        allc = [torch.zeros_like(tc) for _ in range(world)]
+        dist.all_gather(allc, tc)
+        e2e_checks = [float(c.item()) for c in allc]
+
+    # a call of several blocks is ONE launch that walks (tile, block) items: the same metric for calls of mb blocks (the e2e path
+    # above submits F/B blocks per call); the single-block figure above stays the headline `value` (one block per callback is the
+    # real-time contract)
+    multiblock = None
+    mb = min(args.multiblock, e2e_frames // B)
+    if mb > 1 and kb == 1 and len(plan["kernels"]) == 1:
+        ym = torch.empty((n, 2, mb * B), dtype=torch.float32, device=f"cuda:{local}")
+        Rm = R // mb if R >= 2 * mb else 1
+        xm = x if R >= 2 * mb else torch.empty((n, S, 2 * mb * B), dtype=torch.float32, device=f"cuda:{local}")
+        if xm is not x:
+            aw._lib.check(aw.lib().aw_synth_fill_device(local, xm.data_ptr(), rank * n, n, S, 0, 2 * mb * B, SEED, None))
+            Rm = 2
+        Lm = xm.shape[2]
+
+        def mstep(j: int):
+            eng.process_device(xm.data_ptr() + 4 * (j % Rm) * mb * B, S * Lm, Lm, ym.data_ptr(), 2 * mb * B, mb * B, mb * B)
+
+        Km = max(10, K // mb)
+        for j in range(max(3, W // mb)):
+            mstep(j)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(stream)
+        for j in range(Km):
+            mstep(j)
+        m1.record(stream)
+        torch.cuda.synchronize()
+        m_ms = m0.elapsed_time(m1)
+        m_ms = sharding.max_over_ranks(m_ms) if dist is not None else m_ms
+        m_bytes = mb * n * algorithmic_bytes(S, B, P, eq_filters)
+        multiblock = {"blocks_per_call": mb, "calls": Km, "ms_per_call": m_ms / Km, "ms_per_block": m_ms / Km / mb,
+                      "value": world * n * Km * (mb * B / FS) / (m_ms * 1e-3), "unit": UNIT,
+                      "frac_of_peak_by_per_block_algorithmic_bytes": m_bytes / (m_ms / Km * 1e-3) / 1e9 / peak,
+                      "note": "one launch per call; the (tile, block) items of a CTA are walked tile-major, so a tile's FDL rows are "
+                              "re-read from L2 where they still fit"}
+
+    shard = None
+    if world > 1 or args.shard_check:
+        shard = shard_check(aw, torch, dist, rank, world, local, min(n, 512), S, B, (pcm, rate, FS, l_idx, r_idx, B), 4 * B)
+    sync_latency = run_sync_latency(aw, local) if (args.workload == "C1" and rank == 0 and world == 1) else None
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -499,13 +766,19 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * S * F * 4, "d2h_bytes_per_step": n * 2 * F * 4,
                     "frames_per_step": F, "steps": e2e_steps, "timing": "host wall clock around aw_engine_submit..aw_engine_wait, "
                     "synchronised on both sides, max over ranks; copies overlap kernels across steps (2 staging sets)",
-                    "checksum": checksum},
+                    "checksum": checksum, "per_rank_checksum": e2e_checks},
             "gpu_launches": int(c1["kernel_launches"] - c0["kernel_launches"]),
             "host_affinity": affinity,
             "clocks": clocks,
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if multiblock is not None:
+            line["multiblock"] = multiblock
+        if shard is not None:
+            line["sharding"] = shard
+        if sync_latency is not None:
+            line["sync_latency"] = sync_latency
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
@@ -522,6 +795,10 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--blocks-per-call", type=int, default=1, help="blocks per device-resident call of the timed region (a step)")
+    ap.add_argument("--multiblock", type=int, default=4, help="also time calls of this many blocks (0/1 = skip)")
+    ap.add_argument("--shard-check", action="store_true", help="run the sharding bit-identity check even on one GPU")
+    ap.add_argument("--offline-blocks", default="64,128,256,512,1024,2048,4096", help="C5-offline: block sizes of the sweep")
+    ap.add_argument("--offline-seconds", type=float, default=60.0, help="C5-offline: seconds of audio rendered per stream")
     ap.add_argument("--e2e-frames", type=int, default=1024)
     ap.add_argument("--e2e-steps", type=int, default=40)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -529,6 +806,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "C5-offline":
+        return run_offline(args)
     return run_ours(args)
 
 

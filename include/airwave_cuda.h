@@ -146,6 +146,16 @@ AW_API int aw_hesuvi_parse(const char *text, int *left_idx, int *right_idx);
 /* ---- Resampler.resampleHighQuality (Resampler.swift:31-68), computed on `device` ---------- */
 AW_API int aw_resample_output_count(int count, double from_rate, double to_rate);
 AW_API int aw_resample(int device, const float *input, int count, double from_rate, double to_rate, float *output, int capacity, int *written);
+/* Resampling modes.  AW_RESAMPLE_REFERENCE (default everywhere) reproduces Resampler.swift:31-68 literally: the vDSP_vgenp
+ * breakpoints compress a 44.1 kHz response when the target is 48 kHz, the last sample is held, and down-sampling
+ * (where the reference reads past its control vector) is refused with AW_ERR_RESAMPLE_DOWN.
+ * AW_RESAMPLE_CORRECT is the conversion the reference's doc comment describes: out[n] = linear interpolation of the input at
+ * source position n * from_rate / to_rate (float64 position and blend), same output count, last sample held; up- and
+ * down-sampling allowed (no anti-alias filter: meant for impulse responses with little energy above the target Nyquist). */
+#define AW_RESAMPLE_REFERENCE 0
+#define AW_RESAMPLE_CORRECT 1
+AW_API int aw_resample_ex(int device, const float *input, int count, double from_rate, double to_rate, int mode, float *output,
+                          int capacity, int *written);
 
 /* ---- HRIR filter bank: HRIRManager.activatePreset build loop (HRIRManager.swift:347-423) +
  *      ConvolutionEngine.init partitioning/FFT (ConvolutionEngine.swift:68-197), done once per
@@ -155,6 +165,9 @@ AW_API int aw_resample(int device, const float *input, int count, double from_ra
  * If |src_rate - dst_rate| > 0.01 the IRs are resampled with the reference's vgenp semantics. */
 AW_API int aw_bank_create(int device, const float *pcm, int channels, int frames, double src_rate, double dst_rate,
                           const int *left_idx, const int *right_idx, int n_speakers, int block, aw_bank **out);
+/* Same with an explicit resampling mode (AW_RESAMPLE_*). */
+AW_API int aw_bank_create_ex(int device, const float *pcm, int channels, int frames, double src_rate, double dst_rate,
+                             const int *left_idx, const int *right_idx, int n_speakers, int block, int resample_mode, aw_bank **out);
 /* Convenience: load -> layout -> HeSuVi map -> bank, i.e. activatePreset(preset, targetSampleRate, inputLayout). */
 AW_API int aw_bank_create_from_wav(int device, const aw_wav *wav, double dst_rate, int layout, int block, aw_bank **out);
 AW_API int aw_bank_info(const aw_bank *bank, int *n_speakers, int *block, int *partitions, int *taps);

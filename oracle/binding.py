@@ -16,7 +16,7 @@ _LIB_PATH = os.path.join(_HERE, "_build", "libairwave_oracle.so")
 
 __all__ = [
     "build_oracle", "lib", "FFTSetup", "ConvolutionEngine", "VirtualSpeakerRenderer",
-    "RealtimeAudioProcessor", "resample_high_quality", "resample_output_count",
+    "RealtimeAudioProcessor", "resample_high_quality", "resample_linear_f64", "resample_output_count",
     "biquad_make", "BiquadCoefficientError", "ParametricEqualizerState",
     "ParametricEqualizerProcessor", "ParametricEqualizerPreparationError",
     "direct_conv_f64", "synth_fill", "synth_block", "bench_render", "max_threads", "CpuBatch",
@@ -227,6 +227,29 @@ def resample_high_quality(input, fromRate: float, toRate: float) -> np.ndarray:
     if rc == -2:
         raise ValueError("down-sampling reads past the control vector in the reference (undefined)")
     return out[: max(rc, 0)]
+
+
+def resample_linear_f64(input, fromRate: float, toRate: float) -> np.ndarray:
+    """Checker for the flagged AW_RESAMPLE_CORRECT mode (no reference counterpart: Resampler.swift:16-30 documents linear
+    interpolation at the target rate, its vgenp call computes something else — SURVEY.md Q7).  out[n] = input interpolated
+    linearly at source position n * fromRate / toRate, float64 position and blend, last sample held, output count as
+    Resampler.swift:39."""
+    x = _f32(input)
+    if abs(fromRate - toRate) < 0.01:
+        return x
+    n_out = resample_output_count(len(x), fromRate, toRate)
+    if n_out <= 0:
+        return np.zeros(0, np.float32)
+    step = np.float64(fromRate) / np.float64(toRate)
+    pos = np.arange(n_out, dtype=np.float64) * step
+    m = np.minimum(pos.astype(np.int64), len(x) - 2) if len(x) > 1 else np.zeros(n_out, np.int64)
+    xd = x.astype(np.float64)
+    if len(x) == 1:
+        return np.full(n_out, x[0], np.float32)
+    frac = pos - m.astype(np.float64)
+    y = (xd[m] + (xd[m + 1] - xd[m]) * frac).astype(np.float32)
+    y[pos >= len(x) - 1] = x[-1]
+    return y
 
 
 class BiquadCoefficientError(Exception):

@@ -226,3 +226,31 @@ def test_swift_shim_and_module_map_are_shipped():
         assert name in effects, name
     used = set(__import__("re").findall(r"\b(aw_[a-z0-9_]+)\(", effects)) - {"aw_engine_config", "aw_eq_filter"}
     assert used and used <= set(aw.declared_symbols()), used - set(aw.declared_symbols())
+
+
+def test_realtime_path_gate():
+    """The reference gates its render callback with a grep (scripts/check-audio-safety-invariants.sh:23-41: no Array growth,
+    DispatchQueue, locks, print, Logger between BEGIN/END REALTIME CALLBACK).  Same gate for aw_engine_process*: between the
+    BEGIN/END REALTIME PATH markers of aw_api.cu nothing may allocate, grow a container, lock, log or synchronise the device.
+    Lines that only build an error message (set_error) are exempt: they run after the call has already failed."""
+    import re
+    text = open(os.path.join(ROOT, "airwave_b200", "csrc", "aw_api.cu")).read()
+    regions = re.findall(r"// BEGIN REALTIME PATH(.*?)// END REALTIME PATH", text, re.S)
+    assert len(regions) == 2, "markers missing"
+    body = "\n".join(regions)
+    for name in ("process_device_body", "process_block", "eq_process_machine", "aw_engine_process_stereo", "aw_engine_submit_device",
+                 "aw_engine_wait", "eq_begin_call"):
+        assert name + "(" in body, f"{name} is not inside the gated region"
+    forbidden = [r"\bcudaMalloc", r"\bcudaFree\b", r"\bcudaHostAlloc", r"\bcudaFreeHost", r"\bnew\s", r"\bdelete\s", r"push_back", r"emplace_back",
+                 r"\.resize\(", r"\.reserve\(", r"\.insert\(", r"\.erase\(", r"std::vector<", r"std::map", r"std::mutex", r"lock_guard",
+                 r"\bprintf", r"std::cout", r"std::cerr", r"cudaDeviceSynchronize", r"cudaStreamCreate", r"cudaEventCreate\b",
+                 r"std::to_string", r"\bmalloc\(", r"getenv"]
+    bad = []
+    for n, line in enumerate(body.splitlines()):
+        code = line.split("//")[0]
+        if "set_error(" in code:
+            continue
+        for pat in forbidden:
+            if re.search(pat, code):
+                bad.append((pat, line.strip()))
+    assert not bad, bad

@@ -272,6 +272,42 @@ def test_resampler_is_bit_exact_with_the_oracle_and_feeds_the_bank(aw, hrtf_path
     assert np.abs(got - ref).max() <= MAX_ABS and snr_db(ref, got) >= SNR_DB
 
 
+def test_flagged_correct_resampler_mode(aw, hrtf_path):
+    """AW_RESAMPLE_CORRECT (SURVEY.md Q7's flagged alternative to the literal Resampler.swift:31-68): time-correct linear
+    interpolation, bit-exact with the float64 numpy restatement, up- and down-sampling; the literal mode stays the default."""
+    wav_o = oracle.load_wav(hrtf_path("StageSH1.0"))
+    x = wav_o.audioData[3]
+    for src, dst in [(44100.0, 48000.0), (96000.0, 48000.0), (48000.0, 44100.0), (88200.0, 48000.0)]:
+        got = aw.Resampler.resampleHighQuality(x, src, dst, correct=True)
+        want = oracle.resample_linear_f64(x, src, dst)
+        assert len(got) == int(len(x) / (src / dst)) and np.array_equal(got, want), (src, dst)
+    # a slow sinusoid sampled at 44.1 kHz comes out as the same sinusoid sampled at 48 kHz (the literal mode plays it 8.8 % fast)
+    t = np.arange(4410) / 44100.0
+    tone = np.sin(2 * np.pi * 200.0 * t).astype(np.float32)
+    up = aw.Resampler.resampleHighQuality(tone, 44100.0, 48000.0, correct=True)
+    want = np.sin(2 * np.pi * 200.0 * np.arange(len(up)) / 48000.0)
+    assert np.abs(up[:-2] - want[:-2]).max() < 2e-4
+    literal = aw.Resampler.resampleHighQuality(tone, 44100.0, 48000.0)
+    assert np.abs(literal[:4000] - want[:4000]).max() > 0.5
+    # down-sampled bank: 96 kHz -> 48 kHz HRIR (refused in the literal mode), rendered against float64 convolution with the same taps
+    m = aw.HRIRChannelMap.hesuvi14Channel(aw.InputLayout.surround71().channels)
+    sp = aw.InputLayout.surround71().channels
+    l, r = [m.getIndices(s)[0] for s in sp], [m.getIndices(s)[1] for s in sp]
+    with pytest.raises(aw.AirwaveError) as e:
+        aw.HRIRBank(wav_o.audioData, 96000.0, 48000.0, l, r, 256)
+    assert e.value.status == 11
+    bank = aw.HRIRBank(wav_o.audioData, 96000.0, 48000.0, l, r, 256, correct_resampling=True)
+    assert (bank.taps, bank.partitions) == (2160, 9)
+    h = np.stack([np.stack([oracle.resample_linear_f64(wav_o.audioData[l[s]], 96000.0, 48000.0),
+                            oracle.resample_linear_f64(wav_o.audioData[r[s]], 96000.0, 48000.0)]) for s in range(8)])
+    eng = aw.BinauralEngine(1, 8, 256, 48000.0, 1024)
+    eng.set_bank(bank)
+    xin = oracle.synth_block(SEED, [5], 8, 0, 16 * 256)
+    got = np.concatenate([eng.process(xin[:, :, a:a + 1024]) for a in range(0, 16 * 256, 1024)], axis=2)[0]
+    ref = oracle.direct_conv_f64(xin[0], h)
+    assert np.abs(got - ref).max() <= MAX_ABS and snr_db(ref, got) >= SNR_DB
+
+
 def test_bank_errors_mirror_the_reference(aw):
     pcm = np.ones((7, 16), np.float32)
     with pytest.raises(aw.AirwaveError) as e:

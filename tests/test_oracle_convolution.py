@@ -188,3 +188,22 @@ def test_resampler_vgenp_semantics():
     assert len(oracle.resample_high_quality(x, 48000.0, 48000.004)) == 4320
     with pytest.raises(ValueError):
         oracle.resample_high_quality(x, 48000.0, 44100.0)
+
+
+def test_flagged_correct_resampler_checker_properties():
+    """oracle.resample_linear_f64 (checker of AW_RESAMPLE_CORRECT): output count as Resampler.swift:39, identity when the rates
+    agree, exact on a linear ramp, endpoints held, and close to scipy's polyphase resampler on a band-limited signal."""
+    import scipy.signal
+    x = np.linspace(-1, 1, 441, dtype=np.float32)
+    y = oracle.resample_linear_f64(x, 44100.0, 48000.0)
+    assert len(y) == int(441 / (44100.0 / 48000.0)) == 480
+    pos = np.arange(480) * (44100.0 / 48000.0)
+    want = np.where(pos >= 440, 1.0, -1 + pos * (2 / 440))
+    assert np.abs(y - want).max() < 1e-6
+    assert np.array_equal(oracle.resample_linear_f64(x, 48000.0, 48000.004), x)
+    assert len(oracle.resample_linear_f64(x, 96000.0, 48000.0)) == 220
+    t = np.arange(4410) / 44100.0
+    tone = (np.sin(2 * np.pi * 300 * t) * np.hanning(4410)).astype(np.float32)
+    lin = oracle.resample_linear_f64(tone, 44100.0, 48000.0)
+    poly = scipy.signal.resample_poly(tone.astype(np.float64), 160, 147)[: len(lin)]
+    assert np.abs(lin - poly).max() < 2e-3

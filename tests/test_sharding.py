@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 from conftest import ROOT
 
-from airwave_b200.sharding import gather_outputs, max_over_ranks, owner_of, stream_shard
+from airwave_b200.sharding import gather_outputs, gather_samples, max_over_ranks, owner_of, sample_streams, stream_shard
 
 
 @pytest.mark.parametrize("n,world", [(4096, 1), (4096, 2), (4096, 8), (16384, 8), (37, 4), (5, 8), (0, 3)])
@@ -49,8 +49,10 @@ def _worker(rank, world, port, n, frames, q):
         dist.barrier()
         full = gather_outputs(local.astype(np.float32), n)
         slow = max_over_ranks(1.0 + rank)
+        ids = sample_streams(n, world)
+        rows = gather_samples(local.astype(np.float32), n, ids)
         if rank == 0:
-            q.put((full, slow))
+            q.put((full, slow, ids, rows))
     finally:
         dist.destroy_process_group()
 
@@ -64,7 +66,7 @@ def test_two_rank_gloo_gather_reassembles_streams_in_order(n):
     procs = [ctx.Process(target=_worker, args=(r, world, port, n, frames, q)) for r in range(world)]
     for p in procs:
         p.start()
-    full, slow = q.get(timeout=120)
+    full, slow, ids, rows = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -72,3 +74,7 @@ def test_two_rank_gloo_gather_reassembles_streams_in_order(n):
     want = g * 10 + np.arange(2, dtype=np.float32)[None, :, None] + np.arange(frames, dtype=np.float32)[None, None, :] / 100
     assert full.shape == (n, 2, frames) and np.array_equal(full, want.astype(np.float32))
     assert slow == 2.0
+    # the sampled rows arrive from their owners unchanged (a negative zero or NaN payload would not survive a sum with zeros,
+    # audio samples do: x + 0.0 == x bit for bit except -0.0, which compares equal)
+    assert ids == sorted(set(ids)) and ids[0] == 0 and ids[-1] == n - 1
+    assert np.array_equal(rows, want.astype(np.float32)[ids])
