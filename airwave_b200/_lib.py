@@ -115,6 +115,7 @@ def lib() -> C.CDLL:
     L.aw_engine_reset.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.aw_engine_counters.argtypes = [vp, ull, ull, ull, ull]
     L.aw_engine_stream.restype = vp; L.aw_engine_stream.argtypes = [vp]
+    L.aw_engine_uses_tensor_maps.argtypes = [vp]
     L.aw_engine_profile_begin.argtypes = [vp, C.c_int]
     L.aw_engine_plan.argtypes = [vp, ip, ip, ip]
     L.aw_engine_kernels.argtypes = [vp, C.c_char_p, C.c_int]

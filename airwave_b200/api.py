@@ -346,7 +346,8 @@ class BinauralEngine:
     def plan(self) -> dict:
         f, m, p = C.c_int(), C.c_int(), C.c_int()
         L.check(L.lib().aw_engine_plan(self._h, C.byref(f), C.byref(m), C.byref(p)))
-        return dict(fused_tile=f.value, mac_tile=m.value, partitions_cap=p.value, kernels=self.kernels())
+        return dict(fused_tile=f.value, mac_tile=m.value, partitions_cap=p.value, kernels=self.kernels(),
+                    tensor_map_tma=bool(L.lib().aw_engine_uses_tensor_maps(self._h)))
 
     def kernels(self) -> list:
         """Names of the kernels launched per block, in launch order (e.g. ['k_persistent<8,4>'])."""

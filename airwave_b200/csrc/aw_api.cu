@@ -7,6 +7,7 @@
 //               (EqualizerRuntimeEffect.swift:5-78, ParametricEqualizerProcessor.swift:121-408)
 // All streams of an engine advance in lock-step, so adapter counters are per engine.
 // aw_engine_process* allocates nothing: every buffer, stream, event and table is created up front.
+#include <cuda.h>   // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is fetched at run time, libcuda is not linked
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -150,6 +151,7 @@ struct aw_engine {
     float2 *d_fdl = nullptr;
     float *d_fdl_ny = nullptr, *d_overlap = nullptr, *d_pending = nullptr, *d_fifo = nullptr;
     float2 *d_acc = nullptr;
+    void *d_tmaps = nullptr;       // CUtensorMap[RS][3] over d_fdl for KP's stage loads (aw_kernels.h); nullptr = 1-D bulk copies
     double *d_eq_z = nullptr;
     EqProgram *d_eq_prog = nullptr;
     Staging stage[2];
@@ -513,7 +515,7 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
             cudaEvent_t *ev = prof ? &e->profEvents[e->profUsed] : nullptr;
             if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
             AW_LAUNCH(e, launch_persistent(segs, n, e->S, e->P_cap, e->log2m, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl,
-                                           e->d_fdl_ny, out, e->d_tw, e->persistentTile, e->persistentCtas, call, eq, e->stream));
+                                           e->d_fdl_ny, e->d_tmaps, out, e->d_tw, e->persistentTile, e->persistentCtas, call, eq, e->stream));
             if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
         }
         // the remaining nb - 1 decrements of fdlIndex
@@ -726,7 +728,7 @@ void free_engine(aw_engine *e)
     DeviceGuard guard(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     cudaFree(e->d_fdl); cudaFree(e->d_fdl_ny); cudaFree(e->d_overlap); cudaFree(e->d_pending); cudaFree(e->d_fifo);
-    cudaFree(e->d_acc); cudaFree(e->d_eq_z); cudaFree(e->d_eq_prog);
+    cudaFree(e->d_acc); cudaFree(e->d_eq_z); cudaFree(e->d_eq_prog); cudaFree(e->d_tmaps);
     for (Staging &s : e->stage) {
         cudaFree(s.d_in); cudaFree(s.d_out);
         if (s.in_ready) cudaEventDestroy(s.in_ready);
@@ -748,6 +750,47 @@ void free_engine(aw_engine *e)
     delete e;
 }
 
+// Tensor maps over the FDL for KP's stage loads (cp.async.bulk.tensor): one per (rows of a stage part, streams of a tile).
+// Failure is not an error: the kernel then issues one 1-D bulk copy per stream instead.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+void build_fdl_tensor_maps(aw_engine *e)
+{
+    const char *env = getenv("AW_KP_TENSOR_TMA");
+    if (!e->persistent || (env && atoi(env) == 0)) return;
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    const int RS = persistent_stage_rows(e->log2m), bins = persistent_stage_bins(e->log2m);
+    if (RS <= 0 || bins <= 0) return;
+    const cuuint64_t B = (cuuint64_t)e->B, e0 = B < 256 ? B : 256, row_bytes = B * sizeof(float2);
+    // element = one bin (float2, moved as an opaque 64-bit value)
+    const cuuint64_t gdim[5] = {e0, B / e0, (cuuint64_t)e->n, (cuuint64_t)e->P_cap, (cuuint64_t)e->S};
+    const cuuint64_t gstride[4] = {e0 * sizeof(float2), (cuuint64_t)e->S * e->P_cap * row_bytes, row_bytes, (cuuint64_t)e->P_cap * row_bytes};
+    const cuuint32_t estride[5] = {1, 1, 1, 1, 1};
+    std::vector<CUtensorMap> maps((size_t)RS * 3);
+    const int sizes[3] = {4, 2, 1};
+    for (int rows = 1; rows <= RS; ++rows) {
+        for (int k = 0; k < 3; ++k) {
+            const cuuint32_t box[5] = {(cuuint32_t)((cuuint64_t)bins < e0 ? bins : e0), (cuuint32_t)(bins > 256 ? bins / 256 : 1), (cuuint32_t)sizes[k],
+                                       (cuuint32_t)rows, 1};
+            const CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(&maps[(size_t)(rows - 1) * 3 + k], CU_TENSOR_MAP_DATA_TYPE_UINT64, 5, e->d_fdl, gdim,
+                                                                    gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return;
+        }
+    }
+    void *d = nullptr;
+    if (cudaMalloc(&d, maps.size() * sizeof(CUtensorMap)) != cudaSuccess) { cudaGetLastError(); return; }
+    if (cudaMemcpy(d, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return; }
+    e->d_tmaps = d;
+}
+
 int alloc_fdl(aw_engine *e, int P_cap)
 {
     const size_t rows = (size_t)e->n * e->S * P_cap;
@@ -757,6 +800,7 @@ int alloc_fdl(aw_engine *e, int P_cap)
     AW_CUDA(cudaMemsetAsync(e->d_fdl_ny, 0, rows * sizeof(float), e->stream));
     AW_CUDA(cudaStreamSynchronize(e->stream));
     e->P_cap = P_cap;
+    build_fdl_tensor_maps(e);
     return AW_OK;
 }
 
@@ -1119,9 +1163,12 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         const char *q_env = getenv("AW_EQ_FUSION");
         e->eqFusion = q_env && atoi(q_env) != 0;
         e->ringExtra = e->persistent ? 1 : 0;
+        if (const char *v = getenv("AW_KP_RING_EXTRA")) {   // 0: the reference's modulus P; then a call is one launch per block
+            if (atoi(v) == 0) { e->ringExtra = 0; e->kpMultiBlock = false; }
+        }
         if (const char *v = getenv("AW_KP_ORDER")) e->kpOrder = atoi(v) != 0;
         if (const char *v = getenv("AW_KP_KEEP")) e->kpKeepPct = std::max(0, std::min(100, atoi(v)));
-        if (const char *v = getenv("AW_KP_MULTIBLOCK")) e->kpMultiBlock = atoi(v) != 0;
+        if (const char *v = getenv("AW_KP_MULTIBLOCK")) e->kpMultiBlock = atoi(v) != 0 && e->ringExtra > 0;
         if (e->persistent) {
             // largest tile (most filter reuse) unless the smaller one loses clearly less to round quantisation
             auto eff = [&](int T) {
@@ -1577,6 +1624,8 @@ extern "C" int aw_engine_kernels(const aw_engine *e, char *names, int capacity)
     memcpy(names, n.c_str(), n.size() + 1);
     return AW_OK;
 }
+
+extern "C" int aw_engine_uses_tensor_maps(const aw_engine *e) { return e && e->d_tmaps ? 1 : 0; }
 
 extern "C" void *aw_engine_stream(const aw_engine *e) { return e ? (void *)e->stream : nullptr; }
 

@@ -84,6 +84,16 @@ __device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gsrc, 
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
+// Tensor-map TMA load of a 5-D box (cp.async.bulk.tensor, SASS UTMALDG): one instruction moves rows x streams x bins of the
+// FDL into a stage, whatever the strides between them in HBM.  `tmap` is the generic address of a CUtensorMap in global memory.
+__device__ __forceinline__ void tma_load_5d_hint(void *smem_dst, const void *tmap, int c0, int c1, int c2, int c3, int c4, uint64_t *bar,
+                                                 uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5, %6}], [%7], %8;" ::
+            "r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
 __device__ __forceinline__ void named_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)

@@ -125,9 +125,15 @@ struct KpCall {
     int keep_pct;           // tile-major: percentage of the history rows loaded with L2 evict_last in all but the last block
     int debug;              // timing experiments; ignored unless the library is built with -DAW_TIMING_EXPERIMENTS
 };
+// Tensor maps of the engine's FDL for KP's stage loads: 128-byte CUtensorMap objects in global memory, indexed
+// (rows - 1) * 3 + {0: 4 streams, 1: 2 streams, 2: 1 stream} for rows = 1..persistent_stage_rows(log2m); nullptr = bulk copies.
+// Tensor: {bin within a 256-bin chunk, chunk, stream, ring slot, speaker}; box: {min(B,256), chunks of a stage column, streams,
+// rows, 1} -> shared memory [row][stream][bins of the stage column].
+int persistent_stage_rows(int log2m);           // RS: consecutive partitions of one speaker per stage
+int persistent_stage_bins(int log2m);           // bins per stage column (2C)
 cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_cap, int log2m, StridedIn cur, StridedIn prev,
-                              float *overlap_save, float2 *fdl, float *fdl_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
-                              const KpCall &call, const EqFuse &eq, cudaStream_t st);
+                              float *overlap_save, float2 *fdl, float *fdl_ny, const void *tmaps, StridedOut out, const float2 *tw,
+                              int tile, int max_ctas, const KpCall &call, const EqFuse &eq, cudaStream_t st);
 
 // Plan layout in global memory: M half-circle twiddles exp(-2*pi*i*k/(2M)) followed by plan_pt_entries(log2m) per-pass
 // twiddles (RegFft::pt_entry layout), M = 2^log2m complex points.

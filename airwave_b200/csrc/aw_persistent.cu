@@ -115,6 +115,7 @@ struct PersistArgs {
     float *overlap_save;
     float2 *fdl;
     float *fdl_ny;
+    const unsigned char *tmaps;  // CUtensorMap[rows - 1][3 tile sizes] of the FDL (see aw_kernels.h), or nullptr: 1-D bulk copies per stream
     StridedOut out;
     const float2 *tw;
     int debug;   // AW_TIMING_EXPERIMENTS builds only: bit 0 skips the forward transforms, bit 1 the inverse transforms, bit 2 keeps the
@@ -123,7 +124,7 @@ struct PersistArgs {
 };
 
 struct TileCtx {                 // what a role needs to know about the tile it works on
-    int s0, nvalid;              // first stream, valid streams (<= T)
+    int s0, nvalid, ts;          // first stream, valid streams, streams of this tile's shape (T, or `small` in the cut last round)
     int S, P, Pm, head, hs;      // renderers, partitions, ring modulus, FDL head slot of block 0, stages per speaker
     const float4 *bank;
     const float *bank_ny;
@@ -141,6 +142,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PersistArgs &a, int tile)
     if (k < d.n_big) c.s0 = d.first_stream + k * T;
     else { c.s0 = d.first_stream + d.n_big * T + (k - d.n_big) * a.small; size = a.small; }
     c.nvalid = min(size, d.first_stream + d.n_streams - c.s0);
+    c.ts = size;
     c.S = d.S; c.P = d.P; c.Pm = d.Pm; c.head = d.head;
     c.hs = MERGED ? (d.P + RS - 1) / RS : (d.P - 1 + RS - 1) / RS;   // stages per speaker (MERGED: head row included)
     c.bank = d.bank; c.bank_ny = d.bank_ny;
@@ -272,16 +274,27 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 if (slot >= tc.Pm) slot -= tc.Pm;            // the ring has Pm = P + 1 slots (Q4: the reference's has P)
                 const int n1 = min(nrows, tc.Pm - slot);     // rows before the ring wraps
                 mbar_wait(&empty[stage], phase ^ 1u);
-                mbar_expect_tx(&full[stage], (unsigned)(nrows * (tc.nvalid + 2) * C * sizeof(float4)));
                 float4 *dst = ring + (size_t)stage * stage_f4;
                 const uint64_t pol = has_head ? pol_keep : ((a.order && b + 1 < nb) ? pol_reuse : pol_stream);
+                if (a.tmaps) {
+                    // one tensor-map copy for the rows of all the tile's streams (two where the ring wraps): [row][stream][bins]
+                    mbar_expect_tx(&full[stage], (unsigned)(nrows * (tc.ts + 2) * C * sizeof(float4)));
+                    const int sidx = tc.ts == 4 ? 0 : (tc.ts == 2 ? 1 : 2);
+                    constexpr int chunks = 2 * C > 256 ? 2 * C / 256 : 1;     // 256-bin chunks per stage column
+                    tma_load_5d_hint(dst, a.tmaps + (size_t)((n1 - 1) * 3 + sidx) * 128, 0, c * chunks, tc.s0, slot, s, &full[stage], pol);
+                    if (RS > 1 && n1 < nrows)
+                        tma_load_5d_hint(dst + (size_t)n1 * tc.ts * C, a.tmaps + (size_t)((nrows - n1 - 1) * 3 + sidx) * 128, 0, c * chunks, tc.s0, 0,
+                                         s, &full[stage], pol);
+                } else {
+                    mbar_expect_tx(&full[stage], (unsigned)(nrows * (tc.nvalid + 2) * C * sizeof(float4)));
 #pragma unroll
-                for (int u = 0; u < T; ++u) {
-                    if (u < tc.nvalid) {                     // a partial tile moves (and waits for) only the rows it has
-                        const float4 *row = fdl4 + (size_t)(tc.s0 + u) * stream_stride + (size_t)s * a.P_cap * halfB + c * C;
-                        bulk_g2s_hint(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage], pol);
-                        if (RS > 1 && n1 < nrows)
-                            bulk_g2s_hint(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage], pol);
+                    for (int u = 0; u < T; ++u) {
+                        if (u < tc.nvalid) {                 // a partial tile moves (and waits for) only the rows it has
+                            const float4 *row = fdl4 + (size_t)(tc.s0 + u) * stream_stride + (size_t)s * a.P_cap * halfB + c * C;
+                            bulk_g2s_hint(dst + (u * RS) * C, row + (size_t)slot * halfB, (unsigned)(n1 * C * sizeof(float4)), &full[stage], pol);
+                            if (RS > 1 && n1 < nrows)
+                                bulk_g2s_hint(dst + (u * RS + n1) * C, row, (unsigned)((nrows - n1) * C * sizeof(float4)), &full[stage], pol);
+                        }
                     }
                 }
                 const float4 *frow = tc.bank + ((size_t)s * tc.P + p0) * M;
@@ -311,6 +324,8 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
         for (int item = 0; item < n_items; ++item) {
             // first head stage of / stages per column chunk (MERGED: no separate head stages)
             const int hs = tc.hs, head0 = tc.S * hs, spc = MERGED ? head0 : head0 + tc.S;
+            // where stream u's copy of row r sits in a stage: tensor-map loads give [row][stream], bulk copies [stream][row]
+            const int x_us = a.tmaps ? C : RS * C, x_rs = a.tmaps ? tc.ts * C : C;
             for (int c = 0; c < NC; ++c) {
                 int jj = hs > 0 ? m % hs : 0;                // history group of my next stage (RS > 1 only)
                 float4 aL[CW][T], aR[CW][T];
@@ -334,7 +349,7 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                                 const float4 h0 = src[T * RS * C + (row * 2) * C + col], h1 = src[T * RS * C + (row * 2 + 1) * C + col];
                                 float4 x[T];
 #pragma unroll
-                                for (int u = 0; u < T; ++u) x[u] = src[(u * RS + row) * C + col];
+                                for (int u = 0; u < T; ++u) x[u] = src[u * x_us + row * x_rs + col];
 #pragma unroll
                                 for (int u = 0; u < T; ++u) {
                                     cmac2f(aL[v][u], x[u], h0.x, h0.y, h1.x, h1.y);
@@ -551,6 +566,9 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
             // warps, and handed over through `part` (double-buffered by item parity).  The barrier also orders every read of
             // the Nyquist side array before the forward transforms two items ahead, which overwrite this block's oldest slot.
             float *ny_part = part + (item & 1) * 2 * T;
+#ifdef AW_EXP_OLD_NYQUIST
+            if constexpr (G < 32)
+#endif
             for (int idx = fwarp; idx < 2 * T; idx += FFT_WARPS) {
                 const int ls = idx >> 1, ear = idx & 1;
                 float sum = 0.f;
@@ -570,6 +588,9 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 sum = group_sum(sum, 32);
                 if (lane == 0) ny_part[idx] = sum;
             }
+#ifdef AW_EXP_OLD_NYQUIST
+            if constexpr (G < 32)
+#endif
             named_sync(BAR_EQ, PG::FFT_THREADS);
             for (int base = 0; base < 2 * T; base += NFT) {
                 if (base + warp_first_f >= 2 * T) continue;          // warp-uniform: no transform of this warp has work
@@ -579,7 +600,13 @@ __global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const
                 const int stream = s0 + (active ? ls : 0);
                 // idle transforms of a working warp run on their (free) forward buffer so the warp stays converged
                 float2 *buf = idx < 2 * T ? accbuf + (size_t)idx * PS : fftbuf + (size_t)f * PS;
+#ifdef AW_EXP_OLD_NYQUIST
+                float ny;
+                if constexpr (G < 32) ny = idx < 2 * T ? ny_part[idx] : 0.f;
+                else ny = nyquist_sum<G>(g, a.fdl_ny, tc.bank_ny, stream, ear, active, t, part + (size_t)f * G, gb);
+#else
                 const float ny = idx < 2 * T ? ny_part[idx] : 0.f;
+#endif
                 if (gw == 0) {
                     float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs + (size_t)b * M;
                     inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
@@ -683,9 +710,35 @@ int persistent_tiles(int log2m)
     return 0;
 }
 
+int persistent_stage_rows(int log2m)
+{
+    switch (log2m) {
+    case 6: return PGeo<6, 2>::RS;
+    case 7: return PGeo<7, 2>::RS;
+    case 8: return PGeo<8, 2>::RS;
+    case 9: return PGeo<9, 2>::RS;
+    case 10: return PGeo<10, 2>::RS;
+    case 11: return PGeo<11, 2>::RS;
+    default: return 0;
+    }
+}
+
+int persistent_stage_bins(int log2m)
+{
+    switch (log2m) {
+    case 6: return 2 * PGeo<6, 2>::C;
+    case 7: return 2 * PGeo<7, 2>::C;
+    case 8: return 2 * PGeo<8, 2>::C;
+    case 9: return 2 * PGeo<9, 2>::C;
+    case 10: return 2 * PGeo<10, 2>::C;
+    case 11: return 2 * PGeo<11, 2>::C;
+    default: return 0;
+    }
+}
+
 cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_cap, int log2m, StridedIn cur, StridedIn prev,
-                              float *overlap_save, float2 *fdl, float *fdl_ny, StridedOut out, const float2 *tw, int tile, int max_ctas,
-                              const KpCall &call, const EqFuse &eq, cudaStream_t st)
+                              float *overlap_save, float2 *fdl, float *fdl_ny, const void *tmaps, StridedOut out, const float2 *tw,
+                              int tile, int max_ctas, const KpCall &call, const EqFuse &eq, cudaStream_t st)
 {
     if (n_segs <= 0) return cudaSuccess;
     if (n_segs > kKpMaxSegments || !(persistent_tiles(log2m) & tile) || call.nb < 1 || max_ctas < 1) return cudaErrorInvalidValue;
@@ -717,6 +770,7 @@ cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_c
     a.n_segs = n_segs; a.n_tiles = tiles; a.small = small; a.Se = Se; a.P_cap = P_cap;
     a.nb = call.nb; a.order = call.order ? 1 : 0; a.keep_pct = call.keep_pct;
     a.cur = cur; a.prev = prev; a.overlap_save = overlap_save; a.fdl = fdl; a.fdl_ny = fdl_ny; a.out = out; a.tw = tw;
+    a.tmaps = static_cast<const unsigned char *>(tmaps);
     a.debug = call.debug; a.eq = eq;
     const int grid = tiles < max_ctas ? tiles : max_ctas;
 #define AW_KP(L, TT) return launch_persistent_lt<L, TT>(a, grid, st)

@@ -252,6 +252,9 @@ AW_API int aw_engine_profile_begin(aw_engine *engine, int max_blocks);
 AW_API int aw_engine_profile_end(aw_engine *engine, double *kernel_ms, unsigned long long *kernel_launches);
 /* Semicolon-separated names of the kernels the engine launches per block, in launch order (e.g. "k_persistent<8,4>"). */
 AW_API int aw_engine_kernels(const aw_engine *engine, char *names, int capacity);
+/* 1 when the block kernel stages the FDL with tensor-map TMA copies (cp.async.bulk.tensor), 0 when it uses 1-D bulk copies
+ * (driver without cuTensorMapEncodeTiled, or AW_KP_TENSOR_TMA=0).  Diagnostics only. */
+AW_API int aw_engine_uses_tensor_maps(const aw_engine *engine);
 /* Raw CUDA stream (cudaStream_t) the engine launches on, for event timing by the caller. */
 AW_API void *aw_engine_stream(const aw_engine *engine);
 /* Pinned host memory helpers for callers that cannot call cudaHostAlloc themselves. */
