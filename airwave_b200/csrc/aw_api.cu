@@ -141,7 +141,8 @@ struct aw_engine {
     int persistentDebug = 0;       // timing experiments only (AW_PERSISTENT_DEBUG; ignored unless built with -DAW_TIMING_EXPERIMENTS)
     int ringExtra = 0;             // spare FDL ring slots per (stream, speaker): 1 with KP (see KpSegment::Pm), else 0
     int kpOrder = 1;               // walk order of a multi-block call's (tile, block) items: 1 = tile-major, 0 = block-major
-    int kpKeepPct = 50;            // tile-major: share of a tile's history rows kept in L2 (evict_last) for its next block
+    int kpKeepPct = 0;             // tile-major: share of a tile's history rows loaded evict_last in all but the last block (AW_KP_KEEP;
+                                   // measured: 0..25 % is best at C2 — plain LRU keeps what fits, pinning more evicts the filter bank)
     bool kpMultiBlock = true;      // one launch per call (AW_KP_MULTIBLOCK=0: one launch per block)
     bool eqFusion = false;         // AW_EQ_FUSION=1: steady-state EQ rides in KP's epilogue.  Off by default: the bit-exact float64
                                    // recurrence needs ~220 cycles per sample, 29 us per 256-frame block on the few FFT warps of a

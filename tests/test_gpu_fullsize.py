@@ -123,15 +123,33 @@ def test_c4_full_chain_8192_streams(aw, hrtf_path, eq_fixture_bytes):
     assert h.shape[2] == 4702
     for i in range(unique, n):
         assert np.array_equal(y[i], y[i % unique]), i
+    # (1) against the reference's own arithmetic — the float32 restatement of RealtimeAudioProcessor/ConvolutionEngine followed by
+    #     the Double biquad cascade (AudioEffectGraph.swift:195-210): BASELINE.json's bound, unscaled
+    # (2) against float64 direct convolution followed by the same cascade: measured and recorded; the cascade's peaking gains
+    #     amplify the convolution's float32 rounding, so the bound there is stated at the cascade's own gain
+    rows = []
     for i in range(unique):
+        rap = oracle.RealtimeAudioProcessor(oracle.activate_preset(wav_o, FS, oracle.InputLayout.surround71, 256), 256, 256, literalStereo=False)
+        conv32 = np.concatenate([np.stack(rap.process_channels([xu[i, sp, b * 256:(b + 1) * 256] for sp in range(8)]))
+                                 for b in range(frames // 256)], axis=1)
+        st32 = oracle.ParametricEqualizerState(definition, FS)
+        ref32 = np.stack(st32.process(conv32[0], conv32[1])).astype(np.float64)
+        e32, s32 = float(np.abs(y[i] - ref32).max()), float(snr_db(ref32, y[i]))
+        assert e32 <= MAX_ABS and s32 >= SNR_DB, (i, e32, s32)
         conv = oracle.direct_conv_f64(xu[i], h)
         st = oracle.ParametricEqualizerState(definition, FS)
         el, er = st.process(conv[0].astype(np.float32), conv[1].astype(np.float32))
         ref = np.stack([el, er]).astype(np.float64)
-        # the EQ's peaking gains amplify the convolution's float32 rounding: compare at the EQ's own scale
         scale = max(1.0, float(np.abs(ref).max() / max(np.abs(conv).max(), 1e-30)))
-        assert np.abs(y[i] - ref).max() <= MAX_ABS * scale, i
-        assert snr_db(ref, y[i]) >= SNR_DB - 6.0, i
+        e64, s64 = float(np.abs(y[i] - ref).max()), float(snr_db(ref, y[i]))
+        rows.append(dict(stream=i, max_abs_vs_float32_reference_chain=e32, snr_db_vs_float32_reference_chain=s32,
+                         max_abs_vs_float64_chain=e64, snr_db_vs_float64_chain=s64, eq_peak_gain=scale))
+        assert e64 <= MAX_ABS * scale and s64 >= SNR_DB - 6.0, (i, e64, s64)
+    evidence = os.environ.get("AW_EVIDENCE_DIR")
+    if evidence and os.path.isdir(evidence):
+        import json
+        with open(os.path.join(evidence, "c4_chain_error.json"), "w") as f:
+            json.dump(dict(workload="C4 full chain, 8192 streams, 24 blocks of 256 frames", bound_max_abs=MAX_ABS, bound_snr_db=SNR_DB, streams=rows), f, indent=1)
 
 
 def test_c3_full_size_1024_streams_long_brir(aw):
