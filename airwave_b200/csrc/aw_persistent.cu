@@ -67,11 +67,20 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int MAC_SETS = LOG2M >= 10 ? 1 : 2;
     static constexpr int MAC_THREADS = MAC_SETS * 128;
     static constexpr int G = RegFft<LOG2M>::G;               // threads per transform
-    static constexpr int FFT_THREADS = LOG2M >= 10 ? 384 : (8 * G <= 128 ? 128 : 256);
+#ifndef AW_KP_LARGE_FFT_THREADS
+#define AW_KP_LARGE_FFT_THREADS 384
+#endif
+#ifndef AW_KP_LARGE_PRODUCERS
+#define AW_KP_LARGE_PRODUCERS 4
+#endif
+#ifndef AW_KP_LARGE_PREFETCH
+#define AW_KP_LARGE_PREFETCH 0
+#endif
+    static constexpr int FFT_THREADS = LOG2M >= 10 ? AW_KP_LARGE_FFT_THREADS : (8 * G <= 128 ? 128 : 256);
     static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
     // producer warps, one issuing lane each.  B >= 512 with T = 4: three, so that the 19 warps get 104 registers each (the MAC
     // threads hold 2 bin pairs x 4 streams x 2 ears of accumulators); at B = 512 the 6 ring slots divide evenly among them.
-    static constexpr int PRODUCERS = LOG2M >= 9 && T == 4 ? 3 : 4;
+    static constexpr int PRODUCERS = LOG2M >= 10 ? AW_KP_LARGE_PRODUCERS : (LOG2M >= 9 && T == 4 ? 3 : 4);
     static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
     static constexpr int PS = PaddedSize<LOG2M>::value;
     static constexpr int stage_f4 = RS * (T + 2) * C;        // FDL [T][RS][C] + filter [RS][2 planes][C] float4
@@ -90,7 +99,7 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr size_t smem = fixed_bytes + (size_t)STAGES * stage_bytes;
     // next round's operands fetched while this round transforms — only where the registers exist (with 96-104 registers per
     // thread at B >= 512 the spills cost more than the exposed latency: measured)
-    static constexpr bool PREFETCH = LOG2M <= 8;
+    static constexpr bool PREFETCH = LOG2M <= 8 || (LOG2M >= 10 && AW_KP_LARGE_PREFETCH);
     static_assert(STAGES >= PRODUCERS && STAGES % MAC_SETS == 0 && (MAC_SETS == 2 || R == 1), "ring geometry");
     static_assert(NC == 1 || RS == 1, "column chunks carry one row per stage");
 };
