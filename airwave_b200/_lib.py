@@ -43,7 +43,7 @@ ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_OUT_OF_MEMORY, ERR_INVALID_BLOCK_SIZE, ERR_F
 ERR_CHANNEL_MAPPING, ERR_NO_RENDERERS, ERR_RANGE, ERR_MISMATCH, ERR_UNSUPPORTED, ERR_RESAMPLE_DOWN, ERR_NOT_READY = 6, 7, 8, 9, 10, 11, 12
 ERR_EQ_INVALID_SAMPLE_RATE, ERR_EQ_NON_FINITE_PREAMP, ERR_EQ_TOO_MANY_FILTERS, ERR_EQ_INVALID_FILTER = 20, 21, 22, 23
 ERR_WAV_READ, ERR_WAV_CHANNEL_COUNT, ERR_WAV_EMPTY, ERR_WAV_UNSUPPORTED_FORMAT, ERR_EQ_PARSE = 30, 31, 32, 33, 40
-ENGINE_LITERAL_STEREO, ENGINE_PIPELINED = 1, 2
+ENGINE_LITERAL_STEREO, ENGINE_PIPELINED, ENGINE_OVERLAP_EQ = 1, 2, 4
 RESET_SPATIAL, RESET_EQ = 1, 2
 RESAMPLE_REFERENCE, RESAMPLE_CORRECT = 0, 1
 LAYOUT_STEREO, LAYOUT_SURROUND51, LAYOUT_SURROUND71, LAYOUT_ATMOS714 = 2, 6, 8, 12
@@ -112,6 +112,7 @@ def lib() -> C.CDLL:
     L.aw_engine_submit.argtypes = [vp, vp, vp, C.c_int]
     L.aw_engine_submit_device.argtypes = [vp, vp, ll, ll, vp, C.c_int]
     L.aw_engine_wait.argtypes = [vp]
+    L.aw_engine_flush.argtypes = [vp]
     L.aw_engine_reset.argtypes = [vp, C.c_int, C.c_int, C.c_int]
     L.aw_engine_counters.argtypes = [vp, ull, ull, ull, ull]
     L.aw_engine_stream.restype = vp; L.aw_engine_stream.argtypes = [vp]

@@ -263,9 +263,10 @@ class BinauralEngine:
 
     def __init__(self, n_streams: int, n_speakers: int, block: int = 512, sample_rate: float = 48000.0,
                  max_frames_per_call: int = 4096, max_partitions: int = 0, device: int = 0, literal_stereo: bool = False,
-                 pipelined: bool = False):
+                 pipelined: bool = False, overlap_eq: bool = False):
         cfg = EngineConfig(device, n_streams, n_speakers, block, sample_rate, max_frames_per_call, max_partitions,
-                           (L.ENGINE_LITERAL_STEREO if literal_stereo else 0) | (L.ENGINE_PIPELINED if pipelined else 0))
+                           (L.ENGINE_LITERAL_STEREO if literal_stereo else 0) | (L.ENGINE_PIPELINED if pipelined else 0)
+                           | (L.ENGINE_OVERLAP_EQ if overlap_eq else 0))
         h = C.c_void_p()
         L.check(L.lib().aw_engine_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -337,6 +338,10 @@ class BinauralEngine:
 
     def wait(self) -> None:
         L.check(L.lib().aw_engine_wait(self._h))
+
+    def flush(self) -> None:
+        """Orders the engine's stream behind an overlapped equalizer still in flight (AW_ENGINE_OVERLAP_EQ)."""
+        L.check(L.lib().aw_engine_flush(self._h))
 
     def counters(self) -> dict:
         v = [C.c_ulonglong() for _ in range(4)]

@@ -168,6 +168,13 @@ struct aw_engine {
     cudaStream_t side[kSideStreams] = {};
     cudaEvent_t forkEvent = nullptr, joinEvent[kSideStreams] = {};
     cudaStream_t eqStream = nullptr;   // where the equalizer of the machine being processed launches (the main stream, or a side stream)
+    // AW_ENGINE_OVERLAP_EQ: every equalizer launch goes to eqSide, ordered behind the call's convolution by evKp; the main stream
+    // picks a call's equalizer up (evEq) one call later, so the float64 cascade of call j runs next to the convolution of call j+1
+    cudaStream_t eqSide = nullptr;
+    cudaEvent_t evKp = nullptr, evEq[2] = {nullptr, nullptr};
+    bool eqPending[2] = {false, false};
+    int eqParity = 0;
+    bool eqRanThisCall = false;
     std::vector<Segment> segments;
     std::vector<EqMachine> machines;
     // EQ state-object pool (host mirror of the programs resident on the device)
@@ -263,6 +270,7 @@ int eq_pool_grow(aw_engine *e)
     // nothing may still be reading the old array: the engine's streams are idle after this
     ce = cudaStreamSynchronize(e->stream);
     for (int k = 0; k < aw_engine::kSideStreams && ce == cudaSuccess; ++k) ce = cudaStreamSynchronize(e->side[k]);
+    if (ce == cudaSuccess && e->eqSide) ce = cudaStreamSynchronize(e->eqSide);
     if (ce == cudaSuccess) ce = cudaMemcpy(d, e->d_eq_prog, sizeof(EqProgram) * cap, cudaMemcpyDeviceToDevice);
     if (ce == cudaSuccess) ce = cudaMemset(d + cap, 0, sizeof(EqProgram) * (grown - cap));
     if (ce != cudaSuccess) { cudaFree(d); return set_error(AW_ERR_CUDA, std::string("equalizer state pool: ") + cudaGetErrorString(ce)); }
@@ -476,6 +484,21 @@ int eq_process_machine(aw_engine *e, EqMachine &m, StridedOut io, int frames)
     return AW_OK;
 }
 
+// ---- overlapped equalizer (AW_ENGINE_OVERLAP_EQ) ------------------------------------------------------------------------
+bool eq_overlap(const aw_engine *e) { return e->eqSide != nullptr && !e->profOn; }
+cudaStream_t eq_base_stream(const aw_engine *e) { return eq_overlap(e) ? e->eqSide : e->stream; }
+
+// Orders the engine's main stream behind every equalizer still in flight on the internal stream.
+int join_deferred_eq(aw_engine *e)
+{
+    for (int p = 0; p < 2; ++p) {
+        if (!e->eqPending[p]) continue;
+        AW_CUDA(cudaStreamWaitEvent(e->stream, e->evEq[p], 0));
+        e->eqPending[p] = false;
+    }
+    return AW_OK;
+}
+
 // ---- nb blocks of UPOLS for every rendering segment (nb > 1: KP only) ------------------------------------------------
 int ring_modulus(const aw_engine *e, const aw_bank *b) { return b->P + e->ringExtra; }
 
@@ -593,14 +616,15 @@ bool any_rendering(const aw_engine *e)
 // RealtimeAudioProcessor.process (RealtimeAudioProcessor.swift:77-119) + AudioEffectGraph routing (:179-246), device side.
 int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, bool dup_mono);
 
-int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, bool dup_mono)
+int process_device_impl(aw_engine *e, StridedIn in, StridedOut out, int frames, bool dup_mono, bool join = false)
 {
     if (frames <= 0) return AW_OK;                                              // :84
     if (frames > e->maxFrames) return set_error(AW_ERR_FRAME_COUNT, "frameCount exceeds maxFramesPerCallback");   // :85
     if (e->poisoned)
         return set_error(AW_ERR_NOT_READY, "a launch of an earlier call failed, engine state is undefined: call aw_engine_reset on the "
                                            "whole engine (AW_RESET_SPATIAL | AW_RESET_EQ) first");
-    const int rc = process_device_body(e, in, out, frames, dup_mono);
+    int rc = process_device_body(e, in, out, frames, dup_mono);
+    if (rc == AW_OK && join) rc = join_deferred_eq(e);   // synchronous entry points: the call's equalizer is part of the call
     if (rc != AW_OK) e->poisoned = true;   // heads / counters / EQ transitions may have advanced past what the device executed
     return rc;
 }
@@ -609,6 +633,10 @@ int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, 
 {
     const int B = e->B;
     const EqFuse no_eq{nullptr, nullptr, 0, 0};
+    const bool overlap = eq_overlap(e);
+    const cudaStream_t eq_base = eq_base_stream(e);
+    e->eqStream = eq_base;
+    e->eqRanThisCall = false;
     // the equalizer's per-call bookkeeping (target observation, retirement, reset) does not depend on the samples: do it first,
     // so that a steady-state cascade can ride in the block kernel's epilogue instead of a separate pass over the output
     for (EqMachine &m : e->machines) {
@@ -682,8 +710,15 @@ int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, 
     for (const EqMachine &m : e->machines) active_machines += m.eqActive && m.hasProcessor;
     const bool fork_eq = fused.n_filters == 0 && active_machines >= 2 && !e->profOn;
     const int lanes = fork_eq ? std::min(active_machines, (int)aw_engine::kSideStreams) : 0;
+    const bool deferred = overlap && fused.n_filters == 0 && active_machines >= 1;
+    if (deferred) {
+        // the call's convolution (and adapter / passthrough kernels) are all enqueued on the main stream: the equalizer follows them on
+        // its own stream, and the main stream moves on to the next call without waiting for it
+        AW_CUDA(cudaEventRecord(e->evKp, e->stream));
+        AW_CUDA(cudaStreamWaitEvent(eq_base, e->evKp, 0));
+    }
     if (fork_eq) {
-        AW_CUDA(cudaEventRecord(e->forkEvent, e->stream));
+        AW_CUDA(cudaEventRecord(e->forkEvent, eq_base));
         for (int k = 0; k < lanes; ++k) AW_CUDA(cudaStreamWaitEvent(e->side[k], e->forkEvent, 0));
     }
     int ordinal = 0, eq_rc = AW_OK;
@@ -701,11 +736,11 @@ int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, 
         }
         if (fork_eq && m.eqActive && m.hasProcessor) e->eqStream = e->side[ordinal++ % lanes];
         eq_rc = eq_process_machine(e, m, out, frames);
-        e->eqStream = e->stream;
+        e->eqStream = eq_base;
         if (eq_rc != AW_OK) break;
     }
     if (eq_rc == AW_OK && n_steady > 0) {
-        const cudaStream_t st = fork_eq ? e->side[ordinal++ % lanes] : e->stream;
+        const cudaStream_t st = fork_eq ? e->side[ordinal++ % lanes] : eq_base;
         cudaError_t le = launch_eq_steady(steady, n_steady, 0, frames, e->d_eq_z, out, st);
         ++e->launches;
         if (le != cudaSuccess) eq_rc = set_error(AW_ERR_CUDA, std::string("launch_eq_steady: ") + cudaGetErrorString(le));
@@ -713,10 +748,24 @@ int process_device_body(aw_engine *e, StridedIn in, StridedOut out, int frames, 
     if (fork_eq) {
         for (int k = 0; k < lanes; ++k) {
             AW_CUDA(cudaEventRecord(e->joinEvent[k], e->side[k]));
-            AW_CUDA(cudaStreamWaitEvent(e->stream, e->joinEvent[k], 0));
+            AW_CUDA(cudaStreamWaitEvent(eq_base, e->joinEvent[k], 0));
         }
     }
     if (eq_rc != AW_OK) return eq_rc;
+    if (deferred) {
+        // this call's equalizer is complete at evEq[parity]; the main stream waits for the PREVIOUS call's now — after this call's
+        // convolution has been enqueued, so the two ran side by side — and for this one at the end of the next call (or in
+        // aw_engine_flush / aw_engine_wait / any synchronous entry point)
+        const int p = e->eqParity;
+        AW_CUDA(cudaEventRecord(e->evEq[p], eq_base));
+        e->eqPending[p] = true;
+        e->eqRanThisCall = true;
+        if (e->eqPending[p ^ 1]) {
+            AW_CUDA(cudaStreamWaitEvent(e->stream, e->evEq[p ^ 1], 0));
+            e->eqPending[p ^ 1] = false;
+        }
+        e->eqParity = p ^ 1;
+    }
     if (prof) { cudaEventRecord(e->profEqEvents[e->profEqUsed + 1], e->stream); e->profEqUsed += 2; }
     return AW_OK;
 }
@@ -745,6 +794,9 @@ void free_engine(aw_engine *e)
         if (e->joinEvent[k]) cudaEventDestroy(e->joinEvent[k]);
     }
     if (e->forkEvent) cudaEventDestroy(e->forkEvent);
+    if (e->eqSide) { cudaStreamSynchronize(e->eqSide); cudaStreamDestroy(e->eqSide); }
+    if (e->evKp) cudaEventDestroy(e->evKp);
+    for (cudaEvent_t ev : e->evEq) if (ev) cudaEventDestroy(ev);
     if (e->stream) cudaStreamDestroy(e->stream);
     if (e->h2d) cudaStreamDestroy(e->h2d);
     if (e->d2h) cudaStreamDestroy(e->d2h);
@@ -1092,6 +1144,11 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
     }
     AW_TRY(cudaEventCreateWithFlags(&e->forkEvent, cudaEventDisableTiming));
     e->eqStream = e->stream;
+    if (config->flags & AW_ENGINE_OVERLAP_EQ) {
+        AW_TRY(cudaStreamCreateWithFlags(&e->eqSide, cudaStreamNonBlocking));
+        AW_TRY(cudaEventCreateWithFlags(&e->evKp, cudaEventDisableTiming));
+        for (cudaEvent_t &ev : e->evEq) AW_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
     const size_t n = e->n, S = e->S, B = e->B;
     AW_TRY(cudaMalloc(&e->d_overlap, n * S * B * sizeof(float)));
     AW_TRY(cudaMalloc(&e->d_pending, n * S * B * sizeof(float)));
@@ -1227,6 +1284,7 @@ extern "C" int aw_engine_set_bank(aw_engine *e, int first, int count, const aw_b
         if (!e->d_fdl) { if ((rc = alloc_fdl(e, bank->P + e->ringExtra)) != AW_OK) return rc; }
         if (bank->P + e->ringExtra > e->P_cap) return set_error(AW_ERR_MISMATCH, "bank has more partitions than the engine's max_partitions");
     }
+    if ((rc = join_deferred_eq(e)) != AW_OK) return rc;
     AW_CUDA(cudaStreamSynchronize(e->stream));
     split_segments(e, first);
     split_segments(e, first + count);
@@ -1293,7 +1351,7 @@ int eq_control(aw_engine *e, int first, int count, double preamp_db, const aw_eq
             eq_assign(e, m.observedTarget, slot);
             m.transitionFrame = 0;
             m.eqActive = true;
-            cudaError_t ze = launch_eq_reset(e->d_eq_z, m.first, m.count, 3, e->stream);
+            cudaError_t ze = launch_eq_reset(e->d_eq_z, m.first, m.count, 3, eq_base_stream(e));
             ++e->launches;
             if (ze != cudaSuccess) return set_error(AW_ERR_CUDA, std::string("launch_eq_reset: ") + cudaGetErrorString(ze));
             continue;
@@ -1388,7 +1446,7 @@ extern "C" int aw_engine_process(aw_engine *e, const float *in, float *out, int 
     if (e->h_in) {   // zero-copy: the kernels read the staged input and write the output over PCIe themselves
         memcpy(e->h_in, in, inBytes);
         const int zrc = process_device_impl(e, StridedIn{e->h_in, (long long)e->S * frames, (long long)frames},
-                                            StridedOut{e->h_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
+                                            StridedOut{e->h_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false, true);
         if (zrc != AW_OK) return zrc;
         AW_CUDA(cudaStreamSynchronize(e->stream));
         memcpy(out, e->h_out, outBytes);
@@ -1398,7 +1456,7 @@ extern "C" int aw_engine_process(aw_engine *e, const float *in, float *out, int 
     }
     AW_CUDA(cudaMemcpyAsync(s.d_in, in, inBytes, cudaMemcpyHostToDevice, e->stream));
     const int rc = process_device_impl(e, StridedIn{s.d_in, (long long)e->S * frames, (long long)frames},
-                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
+                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false, true);
     if (rc != AW_OK) return rc;
     AW_CUDA(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, e->stream));
     AW_CUDA(cudaStreamSynchronize(e->stream));
@@ -1422,7 +1480,7 @@ extern "C" int aw_engine_process_stereo(aw_engine *e, const float *input_left, c
         memcpy(e->h_in, input_left, bytes);
         if (e->S == 2 && !zdup) memcpy(e->h_in + frames, input_right, bytes);
         const int zrc = process_device_impl(e, StridedIn{e->h_in, (long long)e->S * frames, (long long)frames},
-                                            StridedOut{e->h_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, zdup && e->S == 2);
+                                            StridedOut{e->h_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, zdup && e->S == 2, true);
         if (zrc != AW_OK) return zrc;
         AW_CUDA(cudaStreamSynchronize(e->stream));
         // left first, right second: with aliased outputs the right channel wins, as in RealtimeAudioProcessor.swift:181-182
@@ -1436,7 +1494,7 @@ extern "C" int aw_engine_process_stereo(aw_engine *e, const float *input_left, c
     const bool dup = input_right == nullptr;
     if (e->S == 2 && !dup) AW_CUDA(cudaMemcpyAsync(s.d_in + frames, input_right, bytes, cudaMemcpyHostToDevice, e->stream));
     const int rc = process_device_impl(e, StridedIn{s.d_in, (long long)e->S * frames, (long long)frames},
-                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, dup && e->S == 2);
+                                       StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, dup && e->S == 2, true);
     if (rc != AW_OK) return rc;
     // left first, right second: with aliased outputs the right channel wins, as in RealtimeAudioProcessor.swift:181-182
     AW_CUDA(cudaMemcpyAsync(output_left, s.d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
@@ -1468,7 +1526,8 @@ extern "C" int aw_engine_submit(aw_engine *e, const float *in, float *out, int f
     const int rc = process_device_impl(e, StridedIn{s.d_in, (long long)e->S * frames, (long long)frames},
                                        StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
     if (rc != AW_OK) return rc;
-    AW_CUDA(cudaEventRecord(s.compute_done, e->stream));
+    // the staged output is complete where the call's last kernel ran: the equalizer's stream when it is overlapped
+    AW_CUDA(cudaEventRecord(s.compute_done, e->eqRanThisCall ? e->eqSide : e->stream));
     AW_CUDA(cudaStreamWaitEvent(e->d2h, s.compute_done, 0));
     AW_CUDA(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, e->d2h));
     AW_CUDA(cudaEventRecord(s.out_done, e->d2h));
@@ -1493,7 +1552,8 @@ extern "C" int aw_engine_submit_device(aw_engine *e, const float *in, long long 
     const int rc = process_device_impl(e, StridedIn{in, in_stream_stride, in_channel_stride},
                                        StridedOut{s.d_out, (long long)2 * frames, (long long)frames, 0, 0}, frames, false);
     if (rc != AW_OK) return rc;
-    AW_CUDA(cudaEventRecord(s.compute_done, e->stream));
+    // the staged output is complete where the call's last kernel ran: the equalizer's stream when it is overlapped
+    AW_CUDA(cudaEventRecord(s.compute_done, e->eqRanThisCall ? e->eqSide : e->stream));
     AW_CUDA(cudaStreamWaitEvent(e->d2h, s.compute_done, 0));
     AW_CUDA(cudaMemcpyAsync(out, s.d_out, outBytes, cudaMemcpyDeviceToHost, e->d2h));
     AW_CUDA(cudaEventRecord(s.out_done, e->d2h));
@@ -1506,10 +1566,19 @@ extern "C" int aw_engine_wait(aw_engine *e)
 {
     if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
     DeviceGuard guard(e->cfg.device);
+    const int jrc = join_deferred_eq(e);
+    if (jrc != AW_OK) return jrc;
     AW_CUDA(cudaStreamSynchronize(e->h2d));
     AW_CUDA(cudaStreamSynchronize(e->stream));
     AW_CUDA(cudaStreamSynchronize(e->d2h));
     return AW_OK;
+}
+
+extern "C" int aw_engine_flush(aw_engine *e)
+{
+    if (!e) return set_error(AW_ERR_INVALID_ARGUMENT, "null engine");
+    DeviceGuard guard(e->cfg.device);
+    return join_deferred_eq(e);
 }
 
 // END REALTIME PATH

@@ -390,6 +390,13 @@ cudaError_t launch_eq_steady(const EqSegment *segs, int n_segs, int seg_start, i
     if (warps == 0) return cudaSuccess;
     a.n_segs = n_segs; a.seg_start = seg_start; a.seg_len = seg_len; a.total_warps = warps;
     static const bool pdl = !(getenv("AW_PDL") && atoi(getenv("AW_PDL")) == 0);
+    static bool carveout_set[64] = {};   // same carve-out as the block kernel, next to which this kernel's CTAs run (AW_ENGINE_OVERLAP_EQ)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !carveout_set[dev]) {
+        cudaFuncSetAttribute(k_eq_systolic, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        carveout_set[dev] = true;
+    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)((warps + 3) / 4));
     cfg.blockDim = dim3(128);

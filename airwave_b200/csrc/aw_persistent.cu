@@ -80,8 +80,18 @@ template <int LOG2M, int T> struct PGeo {
     static constexpr int NFT = FFT_THREADS / G;              // transforms side by side
     // producer warps, one issuing lane each.  B >= 512 with T = 4: three, so that the 19 warps get 104 registers each (the MAC
     // threads hold 2 bin pairs x 4 streams x 2 ears of accumulators); at B = 512 the 6 ring slots divide evenly among them.
-    static constexpr int PRODUCERS = LOG2M >= 10 ? AW_KP_LARGE_PRODUCERS : (LOG2M >= 9 && T == 4 ? 3 : 4);
+#ifndef AW_KP_SMALL_PRODUCERS
+#define AW_KP_SMALL_PRODUCERS 4
+#endif
+    static constexpr int PRODUCERS = LOG2M >= 10 ? AW_KP_LARGE_PRODUCERS : (LOG2M >= 9 && T == 4 ? 3 : (LOG2M <= 8 ? AW_KP_SMALL_PRODUCERS : 4));
     static constexpr int THREADS = 32 * PRODUCERS + MAC_THREADS + FFT_THREADS;
+    // Registers per thread.  The CTA owns the SM, but up to B = 256 it leaves 8 K registers (and 40 KB of shared memory) free:
+    // room for one 128-thread CTA of the equalizer kernel, whose float64 recurrence then runs next to the next call's convolution.
+#ifndef AW_KP_SMALL_MAXNREG
+#define AW_KP_SMALL_MAXNREG 112
+#endif
+    static constexpr int MAXNREG = LOG2M <= 8 ? AW_KP_SMALL_MAXNREG : 96;
+    static_assert(THREADS * MAXNREG <= 65536, "register file");
     static constexpr int PS = PaddedSize<LOG2M>::value;
     static constexpr int stage_f4 = RS * (T + 2) * C;        // FDL [T][RS][C] + filter [RS][2 planes][C] float4
     static constexpr size_t stage_bytes = (size_t)stage_f4 * sizeof(float4);
@@ -159,7 +169,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PersistArgs &a, int tile)
 }
 
 template <int LOG2M, int T>
-__global__ void __launch_bounds__(PGeo<LOG2M, T>::THREADS, 1) k_persistent(const __grid_constant__ PersistArgs a)
+__global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid_constant__ PersistArgs a)
 {
     using PG = PGeo<LOG2M, T>;
     constexpr int M = PG::M, halfB = PG::halfB, C = PG::C, NC = PG::NC, R = PG::R, RT = PG::RT, RS = PG::RS, CW = PG::CW, G = PG::G, NFT = PG::NFT;
@@ -684,6 +694,10 @@ cudaError_t launch_persistent_lt(const PersistArgs &a, int ctas, cudaStream_t st
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_persistent<LOG2M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PGeo<LOG2M, T>::smem);
+        if (e != cudaSuccess) return e;
+        // the SM's shared-memory carve-out at its maximum: whatever this CTA leaves (40 KB up to B = 256) stays usable by a
+        // co-resident CTA of the equalizer kernel (AW_ENGINE_OVERLAP_EQ)
+        e = cudaFuncSetAttribute(k_persistent<LOG2M, T>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }

@@ -554,7 +554,11 @@ def run_ours(args):
     banks = [bank] + [aw.HRIRBank(*hrir_pcm(name), FS, l_idx, r_idx, B, device=local) for name in presets[1:]]
     P, taps = bank.partitions, bank.taps
     e2e_frames = max(B, min(4096, args.e2e_frames // B * B))
-    eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=e2e_frames, max_partitions=P, device=local, pipelined=True)
+    # workloads with an equalizer: its float64 cascade runs on an internal stream next to the next call's convolution
+    # (AW_ENGINE_OVERLAP_EQ; outputs alternate between two buffers, as that mode requires)
+    overlap_eq = args.workload in ("C4", "F3") and not args.serial_eq
+    eng = aw.BinauralEngine(n, S, B, FS, max_frames_per_call=e2e_frames, max_partitions=P, device=local, pipelined=True,
+                            overlap_eq=overlap_eq)
     if len(banks) == 1:
         eng.set_bank(bank)
     else:                                     # 64 ranges, banks alternating: one grid per range, run concurrently on side streams
@@ -582,13 +586,14 @@ def run_ours(args):
     kb = e2e_frames // B if args.blocks_per_call <= 0 else max(1, min(args.blocks_per_call, e2e_frames // B))
     R = max(8, 2 * kb)
     x = torch.empty((n, S, R * B), dtype=torch.float32, device=f"cuda:{local}")
-    y = torch.empty((n, 2, kb * B), dtype=torch.float32, device=f"cuda:{local}")
+    y = torch.empty((2, n, 2, kb * B), dtype=torch.float32, device=f"cuda:{local}")
     aw._lib.check(aw.lib().aw_synth_fill_device(local, x.data_ptr(), rank * n, n, S, 0, R * B, SEED, None))
     torch.cuda.synchronize()
     xp, yp = x.data_ptr(), y.data_ptr()
+    y_alt = 4 * n * 2 * kb * B if overlap_eq else 0          # byte offset of the second output buffer
 
     def step(j: int):
-        eng.process_device(xp + 4 * (j % (R // kb)) * kb * B, S * R * B, R * B, yp, 2 * kb * B, kb * B, kb * B)
+        eng.process_device(xp + 4 * (j % (R // kb)) * kb * B, S * R * B, R * B, yp + (j & 1) * y_alt, 2 * kb * B, kb * B, kb * B)
 
     W = max(args.warmup, 3)
     sampler = ClockSampler(local)
@@ -610,6 +615,8 @@ def run_ours(args):
     ev_start.record(stream)
     for j in range(K):                       # exactly K steps back to back: nothing but the engine's launches between the two events
         step(W + j)
+    if overlap_eq:
+        eng.flush()                          # the last call's equalizer is part of the timed region
     ev_end.record(stream)
     torch.cuda.synchronize()
     t_end = time.time()
@@ -704,7 +711,7 @@ def run_ours(args):
     single = None
     if kb > 1 and args.single_block:
         def sstep(j: int):
-            eng.process_device(xp + 4 * (j % R) * B, S * R * B, R * B, yp, 2 * kb * B, kb * B, B)
+            eng.process_device(xp + 4 * (j % R) * B, S * R * B, R * B, yp + (j & 1) * y_alt, 2 * kb * B, kb * B, B)
 
         Ks = max(20, min(K * kb, 2000))
         for j in range(W):
@@ -717,6 +724,8 @@ def run_ours(args):
         m0.record(stream)
         for j in range(Ks):
             sstep(j)
+        if overlap_eq:
+            eng.flush()
         m1.record(stream)
         torch.cuda.synchronize()
         s_ms = m0.elapsed_time(m1)
@@ -756,7 +765,8 @@ def run_ours(args):
                        "taps": taps, "blocks_per_step": kb, "step": f"{kb} x {B}-frame block(s) for all streams, one call (forward FFT -> FDL multiply-accumulate -> inverse FFT"
                                + (f" -> {eq_filters}-biquad float64 EQ cascade)" if eq_filters else ")"),
                        "l2": f"inputs larger than L2: the FDL working set read every step is {n * 8 * S * B * P / 1e6:.0f} MB (L2 = 126 MB)",
-                       "plan": plan},
+                       "plan": plan, "equalizer": ("overlapped with the next call's convolution (AW_ENGINE_OVERLAP_EQ)" if overlap_eq else
+                                                 ("serial" if eq_filters or args.workload == "F3" else None))},
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms, "blocks_per_launch": kb,
@@ -803,6 +813,7 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="override streams per GPU")
     ap.add_argument("--blocks-per-call", type=int, default=0,
                     help="blocks per device-resident call of the timed region (a step); 0 = the e2e call size, --e2e-frames / block")
+    ap.add_argument("--serial-eq", action="store_true", help="C4/F3: run the equalizer behind its call's convolution on the same stream")
     ap.add_argument("--no-single-block", dest="single_block", action="store_false",
                     help="skip the secondary measurement with one block per call")
     ap.add_argument("--shard-check", action="store_true", help="run the sharding bit-identity check even on one GPU")

@@ -114,6 +114,12 @@ typedef struct aw_engine_config {
 #define AW_ENGINE_DEFAULT 0u
 #define AW_ENGINE_LITERAL_STEREO 1u /* reference-literal RealtimeAudioProcessor: min(renderers, 2), inputs = (left, right) (Q1) */
 #define AW_ENGINE_PIPELINED 2u      /* reserve a second staging set so aw_engine_submit can overlap copies and kernels */
+/* The equalizer of a call (AudioEffectGraph runs it after the spatial effect, AudioEffectGraph.swift:195-210) is launched on an
+ * internal stream and runs next to the convolution of the NEXT call.  Nothing changes for aw_engine_process,
+ * aw_engine_process_stereo, aw_engine_submit, aw_engine_submit_device and aw_engine_wait.  For aw_engine_process_device the output of call j is complete,
+ * in the order of aw_engine_stream(), once the work of call j+1 is, or after aw_engine_flush(): consecutive calls must therefore
+ * write to different output buffers (two, alternating, are enough). */
+#define AW_ENGINE_OVERLAP_EQ 4u
 
 /* ---- library / device ------------------------------------------------------------------- */
 AW_API const char *aw_version(void);
@@ -228,6 +234,9 @@ AW_API int aw_engine_submit(aw_engine *engine, const float *in, float *out, int 
 AW_API int aw_engine_submit_device(aw_engine *engine, const float *in, long long in_stream_stride, long long in_channel_stride,
                                    float *out, int frames);
 AW_API int aw_engine_wait(aw_engine *engine);
+/* Orders aw_engine_stream() behind everything the engine still has in flight on internal streams (AW_ENGINE_OVERLAP_EQ);
+ * does not block the host. */
+AW_API int aw_engine_flush(aw_engine *engine);
 /* Single-stream mirror of StereoAudioProcessing.process (AudioPipeline.swift:3-11) for an engine with n_streams == 1
  * and n_speakers <= 2: input_right may be NULL (mono duplicated), output_left may alias output_right. HOST pointers. */
 AW_API int aw_engine_process_stereo(aw_engine *engine, const float *input_left, const float *input_right, float *output_left,

@@ -290,3 +290,79 @@ def test_graph_spatial_then_equalizer_matches_oracle_chain(aw, hrtf_path, eq_fix
         assert np.abs(gl - ol).max() <= 1e-5 and np.abs(gr - orr).max() <= 1e-5
     g.deactivatePreset()
     assert g.prepare(48000.0, None).noEffectCanRun
+
+
+def test_overlapped_equalizer_changes_no_bit(aw, hrtf_path, eq_fixture_bytes):
+    """AW_ENGINE_OVERLAP_EQ: the equalizer of call j runs on an internal stream next to the convolution of call j+1
+    (AudioEffectGraph's order spatial -> equalizer, AudioEffectGraph.swift:195-210, is kept per call).  Same samples as the
+    serial engine through every entry point: device calls (two alternating output buffers, results picked up one call later as
+    the contract says, the last after aw_engine_flush), the synchronous host call, and the pipelined submit/wait path — with a
+    live target change in the middle, so the crossfade's two voices and the reset of the new voice run on the internal stream."""
+    import torch
+    n, S, B, calls, frames = 300, 8, 256, 7, 1024
+    definition = aw.EqualizerAPOParser.parse(eq_fixture_bytes, "CCA CRA ParametricEq.txt")
+    other = dict(preampDB=-3.0, filters=[make_filter("peaking", 1000.0, 4.0, 1.2), make_filter("lowShelf", 120.0, -2.0, 0.7)])
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), 48000.0, aw.InputLayout.surround71(), B)
+    x = oracle.synth_block(SEED, [7 + 3 * i for i in range(n)], S, 0, calls * frames)
+    xd = torch.from_numpy(x).cuda()
+
+    def device_run(overlap):
+        eng = aw.BinauralEngine(n, S, B, 48000.0, max_frames_per_call=frames, max_partitions=bank.partitions, overlap_eq=overlap)
+        eng.set_bank(bank)
+        eng.eq_prepare(definition)
+        stream = torch.cuda.ExternalStream(eng.cuda_stream)
+        ybuf = [torch.empty((n, 2, frames), dtype=torch.float32, device="cuda") for _ in range(2)]
+        outs = [None] * calls
+        for j in range(calls):
+            if j == 3:
+                eng.eq_update(other)
+            xin = xd[:, :, j * frames:(j + 1) * frames].contiguous()
+            torch.cuda.synchronize()
+            eng.process_device(xin.data_ptr(), S * frames, frames, ybuf[j % 2].data_ptr(), 2 * frames, frames, frames)
+            if overlap:
+                if j > 0:                                  # call j-1 is complete in stream order once call j is
+                    with torch.cuda.stream(stream):
+                        outs[j - 1] = ybuf[(j - 1) % 2].clone()
+            else:
+                with torch.cuda.stream(stream):
+                    outs[j] = ybuf[j % 2].clone()
+        if overlap:
+            eng.flush()
+            with torch.cuda.stream(stream):
+                outs[calls - 1] = ybuf[(calls - 1) % 2].clone()
+        torch.cuda.synchronize()
+        eng.close()
+        return np.concatenate([o.cpu().numpy() for o in outs], axis=2)
+
+    serial = device_run(False)
+    assert np.array_equal(device_run(True), serial)
+
+    def host_run(overlap, pipelined):
+        eng = aw.BinauralEngine(n, S, B, 48000.0, max_frames_per_call=frames, max_partitions=bank.partitions, overlap_eq=overlap,
+                                pipelined=pipelined)
+        eng.set_bank(bank)
+        eng.eq_prepare(definition)
+        if not pipelined:
+            outs = []
+            for j in range(calls):
+                if j == 3:
+                    eng.eq_update(other)
+                outs.append(eng.process(np.ascontiguousarray(x[:, :, j * frames:(j + 1) * frames])))
+            eng.close()
+            return np.concatenate(outs, axis=2)
+        hin = [aw.PinnedBuffer((n, S, frames)) for _ in range(calls)]
+        hout = [aw.PinnedBuffer((n, 2, frames)) for _ in range(calls)]
+        for j in range(calls):
+            hin[j].array[...] = x[:, :, j * frames:(j + 1) * frames]
+        for j in range(calls):
+            if j == 3:
+                eng.eq_update(other)
+            eng.submit(hin[j].array.ctypes.data, hout[j].array.ctypes.data, frames)
+        eng.wait()
+        y = np.concatenate([h.array.copy() for h in hout], axis=2)
+        eng.close()
+        return y
+
+    assert np.array_equal(host_run(True, False), serial)
+    assert np.array_equal(host_run(True, True), serial)
+    assert np.array_equal(host_run(False, True), serial)

@@ -1,15 +1,17 @@
 #!/bin/bash
 # GPU-side (run under gpurun): the round's evidence — one bench line per workload, ncu launch lists of the bench command and
-# one `ncu --set full` capture per dominant kernel.  Reports land in gpurun_out/; tools/ncu_summary.py reads them on the CPU box.
-R=${1:-r01}
+# one `ncu --set full` capture per dominant kernel.  Reports land in gpurun_out/; tools/collect_profiles.py reads them on the CPU box.
+R=${1:-r02}
 mkdir -p gpurun_out
 bash tools/bench_all.sh C2 C1 C3 C4 C5-64 C5-128 C5-512 C5-1024 C5-2048 C5-4096 F3 | tee gpurun_out/${R}_bench_all.txt
 # launch list of the default bench command: skip the 2 x 40 warm-up launches (+ set-up kernels), list 40 launches of the timed region
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 40 --csv --log-file gpurun_out/${R}_launches_C2.csv python bench.py --steps 100 --warmup 40 --no-cpu --e2e-steps 3 > gpurun_out/ncu_launches_C2.log 2>&1; echo "launch list C2 rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 100 -c 40 --csv --log-file gpurun_out/${R}_launches_C2.csv python bench.py --steps 100 --warmup 40 --no-cpu --e2e-steps 3 --no-single-block > gpurun_out/ncu_launches_C2.log 2>&1; echo "launch list C2 rc=$?"
 # C4 launches two kernels per step (KP + EQ): warm-up = 2 x 80 launches + set-up
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 190 -c 40 --csv --log-file gpurun_out/${R}_launches_C4.csv python bench.py --workload C4 --steps 100 --warmup 40 --no-cpu --e2e-steps 3 > gpurun_out/ncu_launches_C4.log 2>&1; echo "launch list C4 rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 190 -c 40 --csv --log-file gpurun_out/${R}_launches_C4.csv python bench.py --workload C4 --steps 100 --warmup 40 --no-cpu --e2e-steps 3 --no-single-block > gpurun_out/ncu_launches_C4.log 2>&1; echo "launch list C4 rc=$?"
 for w in C2 C3 C4 C5-512 C5-64 C5-2048; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persistent -s 45 -c 1 -o gpurun_out/${R}_full_$w -f python bench.py --workload $w --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_$w.log 2>&1; echo "$w rc=$?"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persistent -s 45 -c 1 -o gpurun_out/${R}_full_$w -f python bench.py --workload $w --steps 4 --warmup 41 --no-cpu --e2e-steps 3 --no-single-block > gpurun_out/ncu_$w.log 2>&1; echo "$w rc=$?"
 done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eq_systolic -s 45 -c 1 -o gpurun_out/${R}_full_C4eq -f python bench.py --workload C4 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_C4eq.log 2>&1; echo "C4eq rc=$?"
+# the same kernel with one block per launch (the latency-oriented mode)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persistent -s 45 -c 1 -o gpurun_out/${R}_full_C2k1 -f python bench.py --workload C2 --blocks-per-call 1 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_C2k1.log 2>&1; echo "C2k1 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eq_systolic -s 45 -c 1 -o gpurun_out/${R}_full_C4eq -f python bench.py --workload C4 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 --no-single-block > gpurun_out/ncu_C4eq.log 2>&1; echo "C4eq rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_input_rfft -s 45 -c 1 -o gpurun_out/${R}_full_C5-4096_k2 -f python bench.py --workload C5-4096 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_k2.log 2>&1; echo "K2 rc=$?"

@@ -13,7 +13,11 @@ definition = aw.EqualizerAPOParser.parse(eqtxt, "f")
 rng = np.random.default_rng(0)
 for block, n, env in [(64, 9, {}), (128, 9, {}), (256, 21, {}), (512, 9, {}), (1024, 5, {}), (2048, 3, {}), (4096, 2, {}),
                       (256, 9, {"AW_PERSISTENT": "0"}), (256, 9, {"AW_FUSED_TILE": "0"}), (256, 9, {"AW_EQ_FUSION": "1"}),
-                      (256, 13, {"AW_PERSISTENT_CTAS": "2"}), (256, 700, {}), (512, 650, {}), (64, 640, {}), (1024, 301, {})]:
+                      (256, 13, {"AW_PERSISTENT_CTAS": "2"}), (256, 700, {}), (512, 650, {}), (64, 640, {}), (1024, 301, {}),
+                      # round 2: bulk-copy fallback, block-major walk, one launch per block, staged copies instead of zero-copy,
+                      # the reference's ring modulus
+                      (256, 21, {"AW_KP_TENSOR_TMA": "0"}), (64, 37, {"AW_KP_TENSOR_TMA": "0"}), (128, 300, {"AW_KP_ORDER": "0"}),
+                      (256, 9, {"AW_KP_MULTIBLOCK": "0"}), (64, 9, {"AW_ZERO_COPY": "0"}), (512, 9, {"AW_KP_RING_EXTRA": "0"})]:
     os.environ.update(env)
     bank = aw.HRIRBank.from_wav(wav, FS, aw.InputLayout.surround71(), block)
     eng = aw.BinauralEngine(n, 8, block, FS, max_frames_per_call=min(4096, 2 * block))
