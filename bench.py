@@ -220,7 +220,16 @@ def cpu_filters(S, pcm, rate, l_idx, r_idx):
     return h
 
 
-def cpu_sample(S, B, pcm, rate, l_idx, r_idx, budget_s, threads=0):
+def cpu_eq_definition(workload: str):
+    """The reference arm's equalizer for the full-chain workload (parsed by the oracle's parser: no CUDA library involved)."""
+    if workload != "C4":
+        return None
+    import oracle
+    with open(os.path.join(GOLDEN, "eq", "CCA CRA ParametricEq.txt"), "rb") as f:
+        return oracle.parse_equalizer_apo(f.read(), "CCA CRA ParametricEq.txt")
+
+
+def cpu_sample(S, B, pcm, rate, l_idx, r_idx, budget_s, threads=0, eq_definition=None):
     """Times the oracle (C restatement of the reference) on a bounded sample of the workload."""
     import numpy as np
     import oracle
@@ -228,6 +237,8 @@ def cpu_sample(S, B, pcm, rate, l_idx, r_idx, budget_s, threads=0):
     cores = oracle.max_threads() if threads <= 0 else threads
     streams = max(cores * 4, 8)
     batch = oracle.CpuBatch(streams, S, B, h)
+    if eq_definition is not None:
+        batch.set_eq(eq_definition, FS)
     sec, _ = batch.step(2, cores)                          # pilot (also warms the FDL)
     per_block = max(sec / 2, 1e-6)
     blocks = int(max(4, min(200000, budget_s / per_block)))     # ~budget_s seconds of CPU work
@@ -250,7 +261,10 @@ def run_reference(args):
     P = -(-taps // B)
     cores = oracle.max_threads()
     streams = max(cores * 4, 8)
+    eq_def = cpu_eq_definition(args.workload)
     batch = oracle.CpuBatch(streams, S, B, h)
+    if eq_def is not None:
+        batch.set_eq(eq_def, FS)
     # size the per-step sample: long enough (~0.25 s) that thread start-up does not count against the CPU, short enough
     # that the whole --steps/--warmup run ends within a few minutes even for long BRIRs
     pilot, _ = batch.step(8, cores)
@@ -261,6 +275,8 @@ def run_reference(args):
     while per_block * blocks_per_step * (args.steps + args.warmup) > 150 and streams > cores:
         streams //= 2
         batch = oracle.CpuBatch(streams, S, B, h)
+        if eq_def is not None:
+            batch.set_eq(eq_def, FS)
         pilot, _ = batch.step(8, cores)
         per_block = max(pilot / 8, 1e-6)
     for _ in range(args.warmup):
@@ -278,7 +294,7 @@ def run_reference(args):
         "config": {"workload": f"{args.workload}: {desc}", "speakers": S, "block": B, "partitions": P, "taps": taps,
                    "note": "reference algorithm (one ConvolutionEngine per speaker x ear, zvmul+zvadd passes) restated in C "
                            "(oracle/airwave_oracle.c); the Swift/vDSP reference cannot run on Linux"
-                           + ("; the EQ cascade is not part of the CPU sample" if args.workload == "C4" else "")},
+                           + ("; full chain: every stream's output goes through its own 10-biquad Double cascade" if eq_def is not None else "")},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -671,7 +687,9 @@ def run_ours(args):
         dom_ms = kernels_ms[dom_name]
         dom_bytes = n * (8 * S * B * P + 16 * B)      # FDL slots read once (P per speaker) + acc written
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    traffic = recorded_traffic(args.workload, dom_name)
+    # the committed ncu capture is of the default call size (profiles/*_traffic.json; "<W>k1" = one block per launch)
+    traffic_key = args.workload if kb == e2e_frames // B else (args.workload + "k1" if kb == 1 else None)
+    traffic = recorded_traffic(traffic_key, dom_name) if traffic_key else None
     # end-to-end: pinned host buffers, every step's input H2D and output D2H inside the timed region
     F = e2e_frames
     n_bufs = 3
@@ -748,11 +766,12 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, cores, sample = cpu_sample(S, B, pcm, rate, l_idx, r_idx, args.cpu_seconds)   # (first bank of the workload)
-        v1, _, sample1 = cpu_sample(S, B, pcm, rate, l_idx, r_idx, min(3.0, args.cpu_seconds), threads=1)   # the reference's own model:
-                                                                                                           # one real-time thread
-        if eq_def is not None:
-            sample += "; convolution only (the EQ cascade is not part of the CPU sample)"
+        cpu_eq = cpu_eq_definition(args.workload)
+        v, cores, sample = cpu_sample(S, B, pcm, rate, l_idx, r_idx, args.cpu_seconds, eq_definition=cpu_eq)   # (first bank of the workload)
+        v1, _, sample1 = cpu_sample(S, B, pcm, rate, l_idx, r_idx, min(3.0, args.cpu_seconds), threads=1, eq_definition=cpu_eq)   # the
+                                                                                       # reference's own model: one real-time thread
+        if cpu_eq is not None:
+            sample += "; full chain (convolution + the 10-biquad Double cascade per stream)"
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "one_thread": {"value": v1, "unit": UNIT, "sample": sample1}}
 

@@ -940,6 +940,7 @@ typedef struct {
     int n_streams, S, B, ring_blocks, next_block;
     or_conv_engine **L, **R;
     or_rap **raps;
+    or_eq_state **eq;   /* optional: one ParametricEqualizerState per stream, applied after the spatial stage (AudioEffectGraph.swift:195-210) */
     float *input;   /* [stream][ring_blocks][S][B], synthesised once */
 } or_batch;
 
@@ -966,6 +967,19 @@ OR_API or_batch *or_batch_create(int n_streams, int S, int B, const float *h, in
     return b;
 }
 
+/* Full chain for the CPU baseline of BASELINE.json configs[3]: every stream gets its own equalizer state. */
+OR_API int or_batch_set_eq(or_batch *b, double preampDB, const double *filters, int n, double sampleRate)
+{
+    if (!b->eq) b->eq = (or_eq_state **)calloc(b->n_streams, sizeof(void *));
+    for (int t = 0; t < b->n_streams; ++t) {
+        int err, ei, ec;
+        if (b->eq[t]) or_eq_state_release(b->eq[t]);
+        b->eq[t] = or_eq_prepare(preampDB, filters, n, sampleRate, &err, &ei, &ec);
+        if (!b->eq[t]) return err;
+    }
+    return 0;
+}
+
 typedef struct { or_batch *b; int blocks; volatile int *next; double sum; } or_batch_job;
 
 static void *or_batch_worker(void *arg)
@@ -985,6 +999,7 @@ static void *or_batch_worker(void *arg)
             const float *in = b->input + (size_t)t * per_stream + (size_t)rb * S * B;
             for (int s = 0; s < S; ++s) ptrs[s] = in + (size_t)s * B;
             or_rap_process(b->raps[t], ptrs, oL, oR, B);
+            if (b->eq) or_eq_state_process(b->eq[t], oL, oR, oL, oR, B);
             sum += (double)oL[B - 1] + (double)oR[0];
         }
     }
@@ -1020,5 +1035,6 @@ OR_API void or_batch_destroy(or_batch *b)
         or_rap_destroy(b->raps[t]);
         for (int s = 0; s < b->S; ++s) { or_conv_destroy(b->L[(size_t)t * b->S + s]); or_conv_destroy(b->R[(size_t)t * b->S + s]); }
     }
+    if (b->eq) { for (int t = 0; t < b->n_streams; ++t) if (b->eq[t]) or_eq_state_release(b->eq[t]); free(b->eq); }
     free(b->L); free(b->R); free(b->raps); free(b->input); free(b);
 }

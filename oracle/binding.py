@@ -80,6 +80,7 @@ def lib() -> C.CDLL:
         L.or_bench_render.restype = C.c_double
         L.or_bench_render.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_int, C.c_uint32, dp]
         L.or_max_threads.restype = C.c_int
+        L.or_batch_set_eq.argtypes = [vp, C.c_double, dp, C.c_int, C.c_double]
         L.or_batch_create.restype = vp
         L.or_batch_create.argtypes = [C.c_int, C.c_int, C.c_int, fp, C.c_int, C.c_int, C.c_uint32]
         L.or_batch_step.restype = C.c_double
@@ -434,6 +435,13 @@ class CpuBatch:
         h = _f32(h)
         self.n_streams, self.S, self.B = n_streams, S, B
         self._h = lib().or_batch_create(n_streams, S, B, _fp(h), h.shape[2], ring_blocks, seed)
+
+    def set_eq(self, definition, sampleRate: float) -> None:
+        """Every stream of the sample gets its own ParametricEqualizerState after the spatial stage (full chain, C4)."""
+        preamp, arr, n = _pack_filters(definition)
+        rc = lib().or_batch_set_eq(self._h, preamp, _dp(arr) if n else None, n, sampleRate)
+        if rc:
+            raise ValueError(f"equalizer definition rejected ({rc})")
 
     def step(self, blocks: int = 1, threads: int = 0):
         chk = C.c_double()

@@ -4,8 +4,10 @@ usage: python tools/collect_profiles.py r01"""
 import collections, csv, io, json, os, re, shutil, subprocess, sys
 
 R = sys.argv[1] if len(sys.argv) > 1 else "r02"
+REP = os.environ.get("AW_REP_DIR", "gpurun_out")
 os.makedirs("profiles", exist_ok=True)
-shutil.copy(f"gpurun_out/{R}_bench_all.txt", f"profiles/{R}_bench_all.txt")
+if os.path.exists(f"gpurun_out/{R}_bench_all.txt"):
+    shutil.copy(f"gpurun_out/{R}_bench_all.txt", f"profiles/{R}_bench_all.txt")
 for name, skip in [("C2", 100), ("C4", 190)]:
     shutil.copy(f"gpurun_out/{R}_launches_{name}.csv", f"profiles/{R}_launches_{name}.csv")
     rows = [r for r in csv.reader(open(f"profiles/{R}_launches_{name}.csv")) if len(r) > 5]
@@ -35,14 +37,14 @@ with open(f"profiles/{R}_ncu_summary.txt", "w") as f:
             "# A launch = one 1024-frame call (C2, C4: 4 blocks; C5-64: 16; C5-512, C3: 2; C5-2048: 1); C2k1 = C2 with one block per launch.\n"
             "# Per-launch times under ncu are cold-cache and serialised (compare shares, not absolutes); bench.py numbers are never taken under ncu.\n")
     for w in workloads:
-        rep = f"gpurun_out/{R}_full_{w}.ncu-rep"
+        rep = f"{REP}/{R}_full_{w}.ncu-rep"
         f.write(f"\n##### workload {w}\n")
         f.write(subprocess.run([sys.executable, "tools/ncu_summary.py", rep], capture_output=True, text=True).stdout)
         f.write("--- top source lines by warp-stall samples\n")
         f.write(subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "k_", "10"], capture_output=True, text=True).stdout)
 out = {}
-for w, kern in [("C2", "k_persistent<8,4>"), ("C3", "k_persistent<9,4>"), ("C4", "k_persistent<8,4>"), ("C5-512", "k_persistent<9,4>"), ("C5-64", "k_persistent<6,4>"), ("C5-2048", "k_persistent<11,2>")]:
-    raw = subprocess.run(["ncu", "-i", f"gpurun_out/{R}_full_{w}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+for w, kern in [("C2", "k_persistent<8,4>"), ("C2k1", "k_persistent<8,4>"), ("C3", "k_persistent<9,4>"), ("C4", "k_persistent<8,4>"), ("C5-512", "k_persistent<9,4>"), ("C5-64", "k_persistent<6,4>"), ("C5-2048", "k_persistent<11,2>")]:
+    raw = subprocess.run(["ncu", "-i", f"{REP}/{R}_full_{w}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h, u, r = rows[0], rows[1], rows[2]
     def val(name):
