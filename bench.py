@@ -496,8 +496,14 @@ def run_offline(args):
         dt = time.perf_counter() - t0
         c1 = eng.counters()
         launches += int(c1["kernel_launches"] - c0["kernel_launches"])
-        checksum = float(hout[(3 + chunks - 1) % 2].array[:, :, -1].astype("float64").sum())
+        last = hout[(3 + chunks - 1) % 2].array
+        checksum = float(last[:, :, -1].astype("float64").sum())
         dt_max = sharding.max_over_ranks(dt) if dist is not None else dt
+        # the whole job's output is reassembled on the host in global stream order ("the host gathers each GPU's
+        # output"); outside the timed region, last 64 frames of the render
+        gathered = sharding.gather_outputs(np.ascontiguousarray(last[:, :, -64:]), world * n) if dist is not None else last[:, :, -64:]
+        gathered_shape = list(gathered.shape) if gathered is not None else None
+        gathered_checksum = float(gathered.astype("float64").sum()) if gathered is not None else None
         # device time per call (events around 40 calls, nothing else on the stream)
         stream = torch.cuda.ExternalStream(st, device=local)
         y = torch.empty((n, 2, F), dtype=torch.float32, device=f"cuda:{local}")
@@ -517,7 +523,8 @@ def run_offline(args):
                  "device_ms_per_block": {"p50": dev_ms / nb, "p99": percentile(per_call, 0.99) / nb},
                  "device_value_per_gpu": n * (F / FS) / (dev_ms * 1e-3),
                  "roofline_frac": nb * n * algorithmic_bytes(S, B, bank.partitions) / (dev_ms * 1e-3) / 1e9 / peak,
-                 "d2h_gbs_per_gpu": n * 2 * F * 4 * chunks / dt_max / 1e9, "kernels": eng.plan()["kernels"], "checksum_rank0": checksum}
+                 "d2h_gbs_per_gpu": n * 2 * F * 4 * chunks / dt_max / 1e9, "kernels": eng.plan()["kernels"], "checksum_rank0": checksum,
+                 "host_gather": {"shape": gathered_shape, "checksum": gathered_checksum}}
         sweep.append(entry)
         eng.close()
         del bank
@@ -651,7 +658,7 @@ def run_ours(args):
     elapsed_ms = ev_start.elapsed_time(ev_end)
     # per-block latency distribution: a separate pass with an event after every step (the events would otherwise sit between
     # the launches of the timed region)
-    KL = min(K, 1000)
+    KL = min(max(K, 200), 1000)              # enough samples for a p99 even when the driver asks for 20 steps
     events = [torch.cuda.Event(enable_timing=True) for _ in range(KL + 1)]
     events[0].record(stream)
     for j in range(KL):

@@ -366,3 +366,26 @@ def test_overlapped_equalizer_changes_no_bit(aw, hrtf_path, eq_fixture_bytes):
     assert np.array_equal(host_run(True, False), serial)
     assert np.array_equal(host_run(True, True), serial)
     assert np.array_equal(host_run(False, True), serial)
+
+
+def test_equalizer_state_pool_grows_with_the_number_of_ranges(aw, hrtf_path):
+    """Per-device profiles: every stream range holds its own ParametricEqualizerState objects (DeviceProfileManager.swift:4-12).
+    1,500 single-stream ranges with their own equalizers need more than the 1,024 program slots an engine starts with: the pool
+    grows in the control path, and what each stream renders is what a one-range engine renders for the same definition."""
+    n, B = 1500, 256
+    bank = aw.HRIRBank.from_wav(aw.WAVLoader.load(hrtf_path("RoomSH1.0")), 48000.0, aw.InputLayout.stereo(), B)
+    eng = aw.BinauralEngine(n, 2, B, 48000.0, max_frames_per_call=1024, max_partitions=bank.partitions)
+    eng.set_bank(bank)
+    defs = [dict(preampDB=-1.0 - (i % 7), filters=[make_filter("peaking", 200.0 + 13.0 * (i % 50), 3.0, 1.0)]) for i in range(n)]
+    for i in range(n):
+        eng.eq_install_state(defs[i], i, 1)
+    x = oracle.synth_block(SEED, [3] * n, 2, 0, 2048)
+    y = np.concatenate([eng.process(np.ascontiguousarray(x[:, :, a:a + 1024])) for a in (0, 1024)], axis=2)
+    eng.close()
+    for i in (0, 6, 511, 1023, 1024, 1499):
+        ref_eng = aw.BinauralEngine(1, 2, B, 48000.0, max_frames_per_call=1024, max_partitions=bank.partitions)
+        ref_eng.set_bank(bank)
+        ref_eng.eq_install_state(defs[i])
+        ref = np.concatenate([ref_eng.process(np.ascontiguousarray(x[:1, :, a:a + 1024])) for a in (0, 1024)], axis=2)
+        ref_eng.close()
+        assert np.array_equal(y[i], ref[0]), i

@@ -125,8 +125,8 @@ def test_c4_full_chain_8192_streams(aw, hrtf_path, eq_fixture_bytes):
         assert np.array_equal(y[i], y[i % unique]), i
     # (1) against the reference's own arithmetic — the float32 restatement of RealtimeAudioProcessor/ConvolutionEngine followed by
     #     the Double biquad cascade (AudioEffectGraph.swift:195-210): BASELINE.json's bound, unscaled
-    # (2) against float64 direct convolution followed by the same cascade: measured and recorded; the cascade's peaking gains
-    #     amplify the convolution's float32 rounding, so the bound there is stated at the cascade's own gain
+    # (2) against float64 direct convolution followed by the same cascade: the same bound, unscaled (measured on B200:
+    #     max-abs 1.8e-7, SNR 133 dB — profiles/r02_c4_chain_error.json)
     rows = []
     for i in range(unique):
         rap = oracle.RealtimeAudioProcessor(oracle.activate_preset(wav_o, FS, oracle.InputLayout.surround71, 256), 256, 256, literalStereo=False)
@@ -144,7 +144,7 @@ def test_c4_full_chain_8192_streams(aw, hrtf_path, eq_fixture_bytes):
         e64, s64 = float(np.abs(y[i] - ref).max()), float(snr_db(ref, y[i]))
         rows.append(dict(stream=i, max_abs_vs_float32_reference_chain=e32, snr_db_vs_float32_reference_chain=s32,
                          max_abs_vs_float64_chain=e64, snr_db_vs_float64_chain=s64, eq_peak_gain=scale))
-        assert e64 <= MAX_ABS * scale and s64 >= SNR_DB - 6.0, (i, e64, s64)
+        assert e64 <= MAX_ABS and s64 >= SNR_DB, (i, e64, s64)
     evidence = os.environ.get("AW_EVIDENCE_DIR")
     if evidence and os.path.isdir(evidence):
         import json
@@ -407,3 +407,24 @@ def test_long_run_does_not_drift(aw, hrtf_path):
         assert np.abs(got - want).max() <= MAX_ABS, (i, best)
         assert snr_db(want, got) >= SNR_DB
         assert np.abs(y[i][:, :4096] - ref[:, :4096]).max() <= MAX_ABS       # before the first ragged call: no delay at all
+
+
+def test_short_responses_with_many_blocks_per_call(aw, hrtf_path):
+    """More blocks in a call than the ring has slots (P = 1, 2, 3 with calls of up to 64 blocks): every slot of a (stream, speaker)
+    is rewritten several times inside one launch, the forward transform always one item ahead."""
+    wav_o = oracle.load_wav(hrtf_path("NeutralSH1.0"))
+    lay = aw.InputLayout.stereo()
+    l, r = _maps(aw, lay)
+    for taps, block, per_call_blocks, n in [(50, 64, 64, 9), (100, 64, 64, 150), (130, 64, 16, 9), (200, 256, 16, 33), (600, 256, 8, 5), (700, 512, 8, 9)]:
+        short = wav_o.audioData[:, :taps].copy()
+        bank = aw.HRIRBank(short, FS, FS, l, r, block)
+        assert bank.partitions == -(-taps // block)
+        blocks = 2 * per_call_blocks
+        xu, y, plan = _render_twins(aw, bank, n, 2, block, blocks=blocks, unique=min(n, 9), per_call=per_call_blocks * block, pcm_lr=None)
+        assert plan["kernels"][0].startswith("k_persistent<"), plan
+        hs = np.stack([np.stack([short[l[s]], short[r[s]]]) for s in range(2)])
+        for i in range(min(n, 9)):
+            ref = oracle.direct_conv_f64(xu[i], hs)
+            assert np.abs(y[i] - ref).max() <= MAX_ABS, (taps, block, per_call_blocks, i)
+        for i in range(9, n):
+            assert np.array_equal(y[i], y[i % 9]), (taps, block, i)
