@@ -481,6 +481,16 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
         const int warp_first_f = G >= 32 ? f : (ft - lane) / G;   // first transform handled by this warp
         const GroupBar gb{BAR_FFT0 + f, G};
 
+        // publish the head slots of an item: generic-proxy global writes -> visible to the producer's async-proxy reads.  The fence
+        // waits for this thread's outstanding stores; from B = 256 (heads are an item's LAST stages) it is issued a little later,
+        // inside the inverse pass of the previous item, when most of them have landed.
+        auto publish_heads = [&](int item) {
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(heads_done + (item & 1))) : "memory");
+        };
+
         auto forward_item = [&](int lt, int b, int item) {
             const TileCtx tc = my_tile(lt);
             const int s0 = tc.s0, nvalid = tc.nvalid;
@@ -551,17 +561,30 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                         active = active_n; stream = stream_n; sp = sp_n;
                     }
                 } else {
+                    // no registers for a second frame: ask L2 for the next round's frame while this one is transformed (one request
+                    // per 128-byte line: 16 consecutive threads of a transform cover one)
+                    auto prefetch = [&](int base) {
+                        const int idx = base + f;
+                        const int ls = idx / tc.S, s = idx - ls * tc.S;
+                        if (idx < nfft && ls < nvalid && (t & 15) == 0) {
+                            const float *prev = prev_b.ptr + (s0 + ls) * prev_b.ss + s * prev_b.cs;
+                            const float *cur = cur_b.ptr + (s0 + ls) * cur_b.ss + s * cur_b.cs;
+#pragma unroll
+                            for (int e = 0; e < F::E; ++e) {
+                                const int i = F::template load_index<0>(t, e);
+                                const float *p = i < M / 2 ? prev + 2 * i : cur + 2 * (i - M / 2);
+                                asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+                            }
+                        }
+                    };
                     for (int base = 0; base < nfft; base += NFT) {
                         fetch(base, v, active, stream, sp);
+                        if (base + NFT < nfft) prefetch(base + NFT);
                         transform(v, active, stream, sp);
                     }
                 }
             }
-            // publish the head slots: generic-proxy global writes -> visible to the producer's async-proxy bulk reads
-            __threadfence();
-            asm volatile("fence.proxy.async;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(heads_done + (item & 1))) : "memory");
+            if (MERGED || item == 0) publish_heads(item);       // wide stages need the head rows first; otherwise see inverse_item
         };
 
         // fused equalizer (ParametricEqualizerState.process, ParametricEqualizerProcessor.swift:58-91): a systolic array across the
@@ -585,9 +608,6 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
             // warps, and handed over through `part` (double-buffered by item parity).  The barrier also orders every read of
             // the Nyquist side array before the forward transforms two items ahead, which overwrite this block's oldest slot.
             float *ny_part = part + (item & 1) * 2 * T;
-#ifdef AW_EXP_OLD_NYQUIST
-            if constexpr (G < 32)
-#endif
             for (int idx = fwarp; idx < 2 * T; idx += FFT_WARPS) {
                 const int ls = idx >> 1, ear = idx & 1;
                 float sum = 0.f;
@@ -607,10 +627,8 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                 sum = group_sum(sum, 32);
                 if (lane == 0) ny_part[idx] = sum;
             }
-#ifdef AW_EXP_OLD_NYQUIST
-            if constexpr (G < 32)
-#endif
             named_sync(BAR_EQ, PG::FFT_THREADS);
+            if (!MERGED && item + 1 < n_items) publish_heads(item + 1);   // the forward pass of the next item was issued before this call
             for (int base = 0; base < 2 * T; base += NFT) {
                 if (base + warp_first_f >= 2 * T) continue;          // warp-uniform: no transform of this warp has work
                 const int idx = base + f;
@@ -619,13 +637,7 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                 const int stream = s0 + (active ? ls : 0);
                 // idle transforms of a working warp run on their (free) forward buffer so the warp stays converged
                 float2 *buf = idx < 2 * T ? accbuf + (size_t)idx * PS : fftbuf + (size_t)f * PS;
-#ifdef AW_EXP_OLD_NYQUIST
-                float ny;
-                if constexpr (G < 32) ny = idx < 2 * T ? ny_part[idx] : 0.f;
-                else ny = nyquist_sum<G>(g, a.fdl_ny, tc.bank_ny, stream, ear, active, t, part + (size_t)f * G, gb);
-#else
                 const float ny = idx < 2 * T ? ny_part[idx] : 0.f;
-#endif
                 if (gw == 0) {
                     float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs + (size_t)b * M;
                     inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); }, gb);
@@ -677,6 +689,7 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
             if (item + 1 < n_items) forward_item(ltn, bn, item + 1);
             mbar_wait_relaxed(acc_ready, (unsigned)(item & 1));
             if (!(dbg & 2)) inverse_item(lt, b, item);
+            else if (!MERGED && item + 1 < n_items) publish_heads(item + 1);   // (timing experiments that skip the inverse pass)
             __syncwarp();
             if (lane == 0) mbar_arrive(acc_free);
             lt = ltn; b = bn;
