@@ -9,13 +9,15 @@
 // ("segment": streams bound to the same bank) of the engine; a tile looks its segment up.
 //
 //   producer warps      (4; 3 at B >= 512 with T = 4) one elected lane each; producer w fills the ring slots w, w+4, ...: FDL rows
-//                       and the matching filter rows go into a shared-memory ring with TMA-class bulk copies (cp.async.bulk ...
-//                       mbarrier::complete_tx).  UBLKCP takes uniform operands (lane-parallel issue would be serialised by the
-//                       compiler), costs its issuing thread ~155 cycles and the copy engine ~40 cycles whatever its size
-//                       (tools/tmabw.cu) — so a stage is few, large copies: RS consecutive partitions of one speaker x C bin
-//                       pairs for the T streams, 4 KB of FDL per stream and copy (consecutive partitions are consecutive ring
-//                       slots: one copy, two at the wrap), the filter rows in one 8 KB copy.  Rows wider than C bin pairs are
-//                       walked in column chunks (accumulators stay in registers for the whole chunk).
+//                       and the matching filter rows go into a shared-memory ring.  A stage = RS consecutive partitions of one
+//                       speaker x C bin pairs for the tile's streams, moved by ONE tensor-map TMA copy (cp.async.bulk.tensor.5d,
+//                       SASS UTMALDG: box = rows x streams x bins, laid down as [row][stream][bins]; two boxes where the ring
+//                       wraps) + one bulk copy for the filter rows, all completing on the slot's `full` mbarrier.  The issue path
+//                       is what limits a CTA's supply rate (a copy costs its issuing thread ~155 cycles whatever its size,
+//                       tools/tmabw.cu; three producers still match four, two lose 6 %), hence few, large copies.  Without
+//                       tensor maps (driver without cuTensorMapEncodeTiled, AW_KP_TENSOR_TMA=0) the FDL rows go by 1-D bulk
+//                       copies, one per stream ([stream][row][bins]).  Rows wider than C bin pairs are walked in column chunks
+//                       (accumulators stay in registers for the whole chunk).
 //   MAC warps           (8; 4 from B = 1024) sets of 128 threads that take alternate stages; a thread owns one bin pair (two at
 //                       B >= 512) of RT rows of the stage for ALL T streams and both ears, so a filter value is read from shared
 //                       memory once per T streams (shared-memory bandwidth is the resource next to HBM here).  full/empty
@@ -26,7 +28,8 @@
 //                       (accumulators handed over through shared memory, acc_ready/acc_free mbarriers).
 //
 // The head partition (p = 0) is streamed like any other row: the FFT warps publish it with a generic->async proxy fence
-// + a monotonic shared-memory count (release/acquire), which a producer checks before it issues a head row of an item.
+// + a shared-memory count per item parity (release/acquire), which a producer checks before it issues a head row of an item —
+// and, for block b > 0 of a call, before any history row (they include head rows written earlier in the same launch).
 // The FDL ring of a (stream, speaker) has P + 1 slots: the forward transform of block b+1 (one item ahead) lands in the slot
 // block b does not read, so the k blocks of a call need no extra synchronisation — forward(i+2) is only issued after
 // inverse(i), i.e. after item i's multiply-accumulate has consumed all its rows.
