@@ -25,9 +25,10 @@ class HRIRBank {
 public:
     // pcm: planar [channels][frames]; speaker i uses channels left[i] / right[i]
     HRIRBank(int device, const std::vector<float> &pcm, int channels, int frames, double src_rate, double dst_rate,
-             const std::vector<int> &left, const std::vector<int> &right, int block)
+             const std::vector<int> &left, const std::vector<int> &right, int block, int resample_mode = AW_RESAMPLE_REFERENCE)
     {
-        check(aw_bank_create(device, pcm.data(), channels, frames, src_rate, dst_rate, left.data(), right.data(), (int)left.size(), block, &h_));
+        check(aw_bank_create_ex(device, pcm.data(), channels, frames, src_rate, dst_rate, left.data(), right.data(), (int)left.size(), block,
+                                resample_mode, &h_));
         aw_bank_info(h_, &speakers, &this->block, &partitions, &taps);
     }
     ~HRIRBank() { aw_bank_destroy(h_); }
@@ -55,6 +56,19 @@ public:
     // in [stream][speaker][frames], out [stream][2][frames], host pointers; returns the aw_status (never throws)
     int process(const float *in, float *out, int frames) noexcept { return aw_engine_process(h_, in, out, frames); }
     int processStereo(const float *l, const float *r, float *ol, float *orr, int frames) noexcept { return aw_engine_process_stereo(h_, l, r, ol, orr, frames); }
+    // device pointers, strides in elements; with AW_ENGINE_OVERLAP_EQ alternate two output buffers and flush() before reading the last
+    int processDevice(const float *in, long long in_ss, long long in_cs, float *out, long long out_ss, long long out_cs, int frames) noexcept
+    {
+        return aw_engine_process_device(h_, in, in_ss, in_cs, out, out_ss, out_cs, frames);
+    }
+    // pipelined offline rendering (AW_ENGINE_PIPELINED): host or device input, host output valid after wait()
+    int submit(const float *in, float *out, int frames) noexcept { return aw_engine_submit(h_, in, out, frames); }
+    int submitDevice(const float *in, long long in_ss, long long in_cs, float *out, int frames) noexcept
+    {
+        return aw_engine_submit_device(h_, in, in_ss, in_cs, out, frames);
+    }
+    int wait() noexcept { return aw_engine_wait(h_); }
+    int flush() noexcept { return aw_engine_flush(h_); }
     void reset(int first, int count, int what = AW_RESET_SPATIAL) { check(aw_engine_reset(h_, first, count, what)); }
     aw_engine *handle() const { return h_; }
 
