@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
     L.aw_bank_create_ex.argtypes = [C.c_int, fp, C.c_int, C.c_int, C.c_double, C.c_double, ip, ip, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
     L.aw_bank_create_from_wav.argtypes = [C.c_int, vp, C.c_double, C.c_int, C.c_int, C.POINTER(vp)]
     L.aw_bank_info.argtypes = [vp, ip, ip, ip, ip]
+    L.aw_bank_rows.argtypes = [vp]
     L.aw_bank_read.argtypes = [vp, fp, fp]
     L.aw_bank_destroy.argtypes = [vp]; L.aw_bank_destroy.restype = None
     L.aw_engine_create.argtypes = [C.POINTER(EngineConfig), C.POINTER(vp)]

@@ -215,6 +215,7 @@ class HRIRBank:
         s, b, p, t = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         L.check(L.lib().aw_bank_info(self._h, C.byref(s), C.byref(b), C.byref(p), C.byref(t)))
         self.n_speakers, self.block, self.partitions, self.taps = s.value, b.value, p.value, t.value
+        self.rows = L.lib().aw_bank_rows(self._h)   # distinct filter pairs (FC and LFE share one): FDL rows per stream
 
     def read(self):
         spec = np.zeros((self.n_speakers, self.partitions, self.block, 4), np.float32)

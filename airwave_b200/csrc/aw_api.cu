@@ -95,6 +95,10 @@ struct aw_bank {
     int device = 0, S = 0, B = 0, log2m = 0, P = 0, taps = 0;
     float4 *d_bank = nullptr;   // [S][P][2 planes: even bins, odd bins][B/2] {L.re, L.im, R.re, R.im}
     float *d_ny = nullptr;      // [S][P][2]
+    // FDL rows for the block kernel: speakers with the same (left, right) channel pair share one (KpRowTable); [1] = one row per
+    // speaker (literal-stereo engines, AW_KP_MERGE_ROWS=0)
+    int R = 0;
+    KpRowTable *d_rows = nullptr;   // [2]
 };
 
 namespace {
@@ -144,6 +148,7 @@ struct aw_engine {
     int kpKeepPct = 0;             // tile-major: share of a tile's history rows loaded evict_last in all but the last block (AW_KP_KEEP;
                                    // measured: 0..25 % is best at C2 — plain LRU keeps what fits, pinning more evicts the filter bank)
     bool kpMultiBlock = true;      // one launch per call (AW_KP_MULTIBLOCK=0: one launch per block)
+    bool kpMergeRows = true;       // speakers that share a filter pair share an FDL row (AW_KP_MERGE_ROWS=0: one row per speaker)
     bool eqFusion = false;         // AW_EQ_FUSION=1: steady-state EQ rides in KP's epilogue.  Off by default: the bit-exact float64
                                    // recurrence needs ~220 cycles per sample, 29 us per 256-frame block on the few FFT warps of a
                                    // CTA — longer than a tile lasts — whereas the separate K5 pass hides it behind 37 warps per SM
@@ -515,7 +520,7 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         // KP: ONE launch walks the tiles of every range (up to kKpMaxSegments per launch), whatever bank each is bound to, and
         // the nb blocks of the call
         KpSegment segs[kKpMaxSegments];
-        const KpCall call{nb, e->kpOrder, e->kpKeepPct, e->persistentDebug};
+        const KpCall call{nb, e->kpOrder, e->kpKeepPct, e->persistentDebug, prev.ptr == e->d_overlap ? 1 : 0};
         size_t i = 0;
         while (i < e->segments.size()) {
             int n = 0;
@@ -525,7 +530,10 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
                 KpSegment &k = segs[n++];
                 k.first_stream = seg.first;
                 k.n_streams = seg.count;
-                k.S = literal ? std::min(seg.bank->S, 2) : seg.bank->S;
+                // rows: merged (FC + LFE share one) unless the engine is reference-literal stereo or merging is switched off
+                const bool merged = e->kpMergeRows && !literal && seg.bank->d_rows != nullptr && seg.bank->R > 0;
+                k.S = literal ? std::min(seg.bank->S, 2) : (merged ? seg.bank->R : seg.bank->S);
+                k.rows = seg.bank->d_rows + (merged ? 0 : 1);
                 k.P = seg.bank->P;
                 k.Pm = ring_modulus(e, seg.bank);
                 k.head = seg.head;
@@ -1046,6 +1054,24 @@ extern "C" int aw_bank_create_ex(int device, const float *pcm, int channels, int
                                                      : launch_resample_vgenp(d_ir, S * 2, frames, (float)(src_rate / dst_rate), d_rs, taps, 0);
         d_src = d_rs;
     }
+    if (e == cudaSuccess && S <= kKpMaxRows) {
+        KpRowTable t[2];
+        memset(t, -1, sizeof(t));
+        int rows = 0;
+        for (int sp = 0; sp < S; ++sp) {
+            int row = -1;
+            for (int k = 0; k < rows && row < 0; ++k)
+                if (l[t[0].spk[k]] == l[sp] && r[t[0].spk[k]] == r[sp] && t[0].src[k][kKpMaxRowSources - 1] < 0) row = k;
+            if (row < 0) { row = rows++; t[0].spk[row] = (signed char)sp; }
+            for (int q = 0; q < kKpMaxRowSources; ++q)
+                if (t[0].src[row][q] < 0) { t[0].src[row][q] = (signed char)sp; break; }
+            t[1].spk[sp] = (signed char)sp;
+            t[1].src[sp][0] = (signed char)sp;
+        }
+        b->R = rows;
+        e = cudaMalloc(&b->d_rows, sizeof(t));
+        if (e == cudaSuccess) e = cudaMemcpy(b->d_rows, t, sizeof(t), cudaMemcpyHostToDevice);
+    }
     if (e == cudaSuccess) e = cudaMalloc(&b->d_bank, sizeof(float4) * (size_t)S * b->P * block);
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ny, sizeof(float) * (size_t)S * b->P * 2);
     if (e == cudaSuccess) e = launch_bank_build(d_src, S, taps, block, log2m, b->P, b->d_bank, b->d_ny, tw, 0);
@@ -1053,7 +1079,7 @@ extern "C" int aw_bank_create_ex(int device, const float *pcm, int channels, int
     cudaFree(d_ir);
     cudaFree(d_rs);
     if (e != cudaSuccess) {
-        cudaFree(b->d_bank); cudaFree(b->d_ny);
+        cudaFree(b->d_bank); cudaFree(b->d_ny); cudaFree(b->d_rows);
         delete b;
         return set_error(e == cudaErrorMemoryAllocation ? AW_ERR_OUT_OF_MEMORY : AW_ERR_CUDA, std::string("aw_bank_create: ") + cudaGetErrorString(e));
     }
@@ -1081,6 +1107,8 @@ extern "C" int aw_bank_info(const aw_bank *bank, int *n_speakers, int *block, in
     return AW_OK;
 }
 
+extern "C" int aw_bank_rows(const aw_bank *bank) { return bank ? bank->R : 0; }
+
 extern "C" int aw_bank_read(const aw_bank *bank, float *spectrum, float *nyquist)
 {
     if (!bank) return set_error(AW_ERR_INVALID_ARGUMENT, "null bank");
@@ -1104,6 +1132,7 @@ extern "C" void aw_bank_destroy(aw_bank *bank)
     DeviceGuard guard(bank->device);
     cudaFree(bank->d_bank);
     cudaFree(bank->d_ny);
+    cudaFree(bank->d_rows);
     delete bank;
 }
 
@@ -1224,6 +1253,7 @@ extern "C" int aw_engine_create(const aw_engine_config *config, aw_engine **out)
         if (const char *v = getenv("AW_KP_RING_EXTRA")) {   // 0: the reference's modulus P; then a call is one launch per block
             if (atoi(v) == 0) { e->ringExtra = 0; e->kpMultiBlock = false; }
         }
+        if (const char *v = getenv("AW_KP_MERGE_ROWS")) e->kpMergeRows = atoi(v) != 0;
         if (const char *v = getenv("AW_KP_ORDER")) e->kpOrder = atoi(v) != 0;
         if (const char *v = getenv("AW_KP_KEEP")) e->kpKeepPct = std::max(0, std::min(100, atoi(v)));
         if (const char *v = getenv("AW_KP_MULTIBLOCK")) e->kpMultiBlock = atoi(v) != 0 && e->ringExtra > 0;

@@ -105,9 +105,18 @@ struct EqFuse {             // equalizer fused into KP's epilogue (steady state 
 };
 bool persistent_can_fuse_eq(int log2m, int tile, int n_filters);
 int persistent_tiles(int log2m);                // bit mask of the tiles available for that transform size (0 = unsupported)
+// FDL rows of a bank.  Speakers that share one (left, right) impulse-response pair — FC and LFE in both HeSuVi maps
+// (VirtualSpeaker.swift:235-236, 281-283) — share ONE row: convolution is linear, so their input channels are
+// added before the forward transform and filtered once (conv(a, h) + conv(b, h) = conv(a + b, h), rounding aside).  A row names
+// the input channels it sums (up to 4, -1 = none) and the bank speaker whose filter rows it uses.
+constexpr int kKpMaxRows = 64, kKpMaxRowSources = 4;
+struct KpRowTable {
+    signed char src[kKpMaxRows][kKpMaxRowSources];
+    signed char spk[kKpMaxRows];
+};
 struct KpSegment {          // a stream range bound to one bank (tile0 and n_big are filled in by the launcher)
     int first_stream, n_streams;
-    int S, P;               // renderers, partitions
+    int S, P;               // FDL rows (distinct renderers, see KpRowTable), partitions
     int Pm;                 // ring modulus of the range's FDL rows: P + 1.  The reference's modulus is partitionCount
                             // (ConvolutionEngine.swift:256-259); the spare slot lets the forward transform of block b+1 be
                             // written while block b's multiply-accumulate still reads its P slots (one launch walks the k
@@ -116,14 +125,16 @@ struct KpSegment {          // a stream range bound to one bank (tile0 and n_big
     int tile0, n_big;       // first tile of the range; its first n_big tiles hold T streams, the rest `small` streams
     const float4 *bank;
     const float *bank_ny;
+    const KpRowTable *rows; // device memory (part of the bank)
 };
-constexpr int kKpMaxSegments = 64;   // per launch (64 x 48 B of the 4 KB kernel parameter space)
+constexpr int kKpMaxSegments = 64;   // per launch (64 x 56 B of the 4 KB kernel parameter space)
 struct KpCall {
     int nb;                 // blocks of this call (frames = nb * B); input block b at cur + b*B, output block b at out + b*B
     int order;              // walk order of the (tile, block) items of a CTA: 0 = block-major (all tiles of block 0, then block
                             // 1, ...), 1 = tile-major (all blocks of a tile back to back: its FDL rows are re-read from L2)
     int keep_pct;           // tile-major: percentage of the history rows loaded with L2 evict_last in all but the last block
     int debug;              // timing experiments; ignored unless the library is built with -DAW_TIMING_EXPERIMENTS
+    int prev_is_rows;       // 1: `prev` is the engine's overlap buffer (one summed block per FDL row); 0: it is laid out like the input
 };
 // Tensor maps of the engine's FDL for KP's stage loads: 128-byte CUtensorMap objects in global memory, indexed
 // (rows - 1) * 3 + {0: 4 streams, 1: 2 streams, 2: 1 stream} for rows = 1..persistent_stage_rows(log2m); nullptr = bulk copies.

@@ -130,7 +130,7 @@ template <int LOG2M, int T> struct PGeo {
 struct PersistArgs {
     int n_segs, n_tiles;
     int small;                   // streams per tile behind a segment's first n_big tiles (T, T/2 or T/4)
-    int nb, order, keep_pct;     // KpCall
+    int nb, order, keep_pct, prev_is_rows;   // KpCall
     int Se, P_cap;               // engine-wide layout of the state arrays (speakers per stream, FDL slots per (stream, speaker))
     KpSegment seg[kKpMaxSegments];
     StridedIn cur, prev;         // block b of the call is cur + b*B; the block before block 0 is prev (inputOverlapBuffer)
@@ -150,6 +150,7 @@ struct TileCtx {                 // what a role needs to know about the tile it 
     int S, P, Pm, head, hs;      // renderers, partitions, ring modulus, FDL head slot of block 0, stages per speaker
     const float4 *bank;
     const float *bank_ny;
+    const KpRowTable *rt;        // which input channels a row sums, whose filter rows it uses
 };
 
 template <int T, int RS, bool MERGED>
@@ -167,7 +168,7 @@ __device__ __forceinline__ TileCtx tile_ctx(const PersistArgs &a, int tile)
     c.ts = size;
     c.S = d.S; c.P = d.P; c.Pm = d.Pm; c.head = d.head;
     c.hs = MERGED ? (d.P + RS - 1) / RS : (d.P - 1 + RS - 1) / RS;   // stages per speaker (MERGED: head row included)
-    c.bank = d.bank; c.bank_ny = d.bank_ny;
+    c.bank = d.bank; c.bank_ny = d.bank_ny; c.rt = d.rows;
     return c;
 }
 
@@ -243,6 +244,7 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
             unsigned phase = 0, seen0 = 0, seen1 = 0;        // last values read from heads_done[0], [1]
             TileCtx tc = my_tile(0);
             int hb = head_of(tc, 0);
+            int bs = tc.rt->spk[0];                          // bank speaker whose filter rows row s uses
             bool hist = MERGED || tc.hs > 0;
             auto new_item = [&]() {
                 const int lt0 = lt;
@@ -268,7 +270,12 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1u; }
             };
-            for (int i = 0; i < warp && item < n_items; ++i) advance();   // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
+            auto advance_to_my_slot = [&](int steps) {
+                const int s0_ = s, item0 = item;
+                for (int i = 0; i < steps && item < n_items; ++i) advance();
+                if (item < n_items && (s != s0_ || item != item0)) bs = tc.rt->spk[s];
+            };
+            advance_to_my_slot(warp);   // producer w owns the ring slots w, w + PRODUCERS, ... < STAGES
             while (item < n_items) {
                 // rows of this stage: partitions p0, p0+1, ... in consecutive ring slots (MERGED: the first stage of a speaker starts
                 // with the head row, p = 0)
@@ -319,7 +326,7 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                         }
                     }
                 }
-                const float4 *frow = tc.bank + ((size_t)s * tc.P + p0) * M;
+                const float4 *frow = tc.bank + ((size_t)bs * tc.P + p0) * M;
                 if (NC == 1) {                               // whole rows: both planes of RS consecutive partitions are contiguous
                     bulk_g2s_hint(dst + T * RS * C, frow, (unsigned)(nrows * 2 * C * sizeof(float4)), &full[stage], pol_keep);
                 } else {
@@ -327,7 +334,7 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                     bulk_g2s_hint(dst + T * C + C, frow + halfB + c * C, (unsigned)(C * sizeof(float4)), &full[stage], pol_keep);
                 }
                 const int step = stage + PRODUCERS < STAGES ? PRODUCERS : STAGES - stage + warp;   // to my next slot
-                for (int i = 0; i < step && item < n_items; ++i) advance();
+                advance_to_my_slot(step);
             }
         }
     } else if (warp < PRODUCERS + MAC_WARPS) {
@@ -335,7 +342,6 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
         const int mt = tid - 32 * PRODUCERS;
         const int set = mt >> 7, w = mt & 127;
         const int r = C < 128 ? w / C : 0, jp = C < 128 ? w - r * C : w;
-        const int contributor = set * R + r;                 // partial sums are reduced in this order
         // set q drains the ring slots of parity q, i.e. the stages k = q, q + 2, ... of the CTA's stage sequence (STAGES is even)
         int stage = set;                                     // ring slot of my next stage
         unsigned phase = 0;
@@ -350,6 +356,9 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
             const int x_us = a.tmaps ? C : RS * C, x_rs = a.tmaps ? tc.ts * C : C;
             for (int c = 0; c < NC; ++c) {
                 int jj = hs > 0 ? m % hs : 0;                // history group of my next stage (RS > 1 only)
+                // Partial sums are reduced in the order (stage parity within the item, row): with an odd number of stages per item
+                // (7 rows) the two sets swap the even and the odd stages from item to item, and the order of the sum must not
+                const int contributor = (PG::MAC_SETS == 2 ? (m & 1) : 0) * R + r;
                 float4 aL[CW][T], aR[CW][T];
 #pragma unroll
                 for (int v = 0; v < CW; ++v)
@@ -503,6 +512,7 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
             const StridedIn cur_b{a.cur.ptr + (size_t)b * M, a.cur.ss, a.cur.cs};
             const StridedIn prev_b = b == 0 ? a.prev : StridedIn{a.cur.ptr + (size_t)(b - 1) * M, a.cur.ss, a.cur.cs};
             float *ov_save = (b == nb - 1) ? a.overlap_save : nullptr;   // inputOverlapBuffer <- the call's last block (:243)
+            const bool prev_rows = b == 0 && a.prev_is_rows;             // the overlap buffer holds one (summed) block per row
             if (!(dbg & 1)) {
                 auto fetch = [&](int base, float2 (&v)[F::E], bool &active, int &stream, int &s) {
                     const int idx = base + f;
@@ -510,13 +520,33 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                     s = idx - ls * tc.S;
                     active = idx < nfft && ls < nvalid;
                     stream = s0 + (active ? ls : 0);
-                    const float *prev = prev_b.ptr + stream * prev_b.ss + s * prev_b.cs;
-                    const float *cur = cur_b.ptr + stream * cur_b.ss + s * cur_b.cs;
+                    // a row sums the input channels that share its filter pair (KpRowTable); the overlap buffer holds the row's
+                    // previous block already summed, the call's own input does not
+                    const signed char *src = tc.rt->src[active ? s : 0];
+                    const int c0 = src[0];
+                    const float *prev = prev_b.ptr + stream * prev_b.ss + (prev_rows ? s : c0) * prev_b.cs;
+                    const float *cur = cur_b.ptr + stream * cur_b.ss + c0 * cur_b.cs;
 #pragma unroll
                     for (int e = 0; e < F::E; ++e) {
                         const int i = F::template load_index<0>(t, e);   // frame = [previous block | current block] (:237-248)
                         v[e] = (!active || (dbg & (4 | 32))) ? make_float2(0.f, 0.f)
                                        : (i < M / 2 ? *reinterpret_cast<const float2 *>(prev + 2 * i) : *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2)));
+                    }
+                    if (active && src[1] >= 0) {                         // warp-uniform per transform: rare (FC + LFE)
+                        for (int q = 1; q < kKpMaxRowSources && src[q] >= 0; ++q) {
+                            const float *pq = prev_b.ptr + stream * prev_b.ss + src[q] * prev_b.cs;
+                            const float *cq = cur_b.ptr + stream * cur_b.ss + src[q] * cur_b.cs;
+#pragma unroll
+                            for (int e = 0; e < F::E; ++e) {
+                                const int i = F::template load_index<0>(t, e);
+                                if (i < M / 2) {
+                                    if (!prev_rows) { const float2 x = *reinterpret_cast<const float2 *>(pq + 2 * i); v[e].x += x.x; v[e].y += x.y; }
+                                } else {
+                                    const float2 x = *reinterpret_cast<const float2 *>(cq + 2 * (i - M / 2));
+                                    v[e].x += x.x; v[e].y += x.y;
+                                }
+                            }
+                        }
                     }
                 };
                 auto transform = [&](float2 (&v)[F::E], bool active, int stream, int sp) {
@@ -570,8 +600,9 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                         const int idx = base + f;
                         const int ls = idx / tc.S, s = idx - ls * tc.S;
                         if (idx < nfft && ls < nvalid && (t & 15) == 0) {
-                            const float *prev = prev_b.ptr + (s0 + ls) * prev_b.ss + s * prev_b.cs;
-                            const float *cur = cur_b.ptr + (s0 + ls) * cur_b.ss + s * cur_b.cs;
+                            const int c0 = tc.rt->src[s][0];
+                            const float *prev = prev_b.ptr + (s0 + ls) * prev_b.ss + (prev_rows ? s : c0) * prev_b.cs;
+                            const float *cur = cur_b.ptr + (s0 + ls) * cur_b.ss + c0 * cur_b.cs;
 #pragma unroll
                             for (int e = 0; e < F::E; ++e) {
                                 const int i = F::template load_index<0>(t, e);
@@ -622,7 +653,7 @@ __global__ void __maxnreg__((PGeo<LOG2M, T>::MAXNREG)) k_persistent(const __grid
                     for (int k = lane; k < n; k += 32) {
                         int slot = g.head + p;
                         if (slot >= tc.Pm) slot -= tc.Pm;
-                        sum = fmaf(xs[(size_t)sp * a.P_cap + slot], tc.bank_ny[(size_t)k * 2 + ear], sum);
+                        sum = fmaf(xs[(size_t)sp * a.P_cap + slot], tc.bank_ny[((size_t)tc.rt->spk[sp] * tc.P + p) * 2 + ear], sum);
                         p += 32;
                         while (p >= tc.P) { p -= tc.P; ++sp; }
                     }
@@ -807,7 +838,7 @@ cudaError_t launch_persistent(const KpSegment *segs, int n_segs, int Se, int P_c
         seen += nt;
     }
     a.n_segs = n_segs; a.n_tiles = tiles; a.small = small; a.Se = Se; a.P_cap = P_cap;
-    a.nb = call.nb; a.order = call.order ? 1 : 0; a.keep_pct = call.keep_pct;
+    a.nb = call.nb; a.order = call.order ? 1 : 0; a.keep_pct = call.keep_pct; a.prev_is_rows = call.prev_is_rows;
     a.cur = cur; a.prev = prev; a.overlap_save = overlap_save; a.fdl = fdl; a.fdl_ny = fdl_ny; a.out = out; a.tw = tw;
     a.tmaps = static_cast<const unsigned char *>(tmaps);
     a.debug = call.debug; a.eq = eq;

@@ -788,7 +788,7 @@ def run_ours(args):
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "streams_per_gpu": n, "speakers": S, "block": B, "partitions": P,
-                       "taps": taps, "blocks_per_step": kb, "step": f"{kb} x {B}-frame block(s) for all streams, one call (forward FFT -> FDL multiply-accumulate -> inverse FFT"
+                       "taps": taps, "fdl_rows": bank.rows, "blocks_per_step": kb, "step": f"{kb} x {B}-frame block(s) for all streams, one call (forward FFT -> FDL multiply-accumulate -> inverse FFT"
                                + (f" -> {eq_filters}-biquad float64 EQ cascade)" if eq_filters else ")"),
                        "l2": f"inputs larger than L2: the FDL working set read every step is {n * 8 * S * B * P / 1e6:.0f} MB (L2 = 126 MB)",
                        "plan": plan, "equalizer": ("overlapped with the next call's convolution (AW_ENGINE_OVERLAP_EQ)" if overlap_eq else
@@ -796,11 +796,15 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms, "blocks_per_launch": kb,
+                         "fdl_rows": bank.rows, "frac_counting_shared_rows":
+                             kb * n * (8 * bank.rows * B * P + 4 * S * B + 8 * B) / (dom_ms * 1e-3) / 1e9 / peak if len(plan["kernels"]) == 1 else None,
                          "hbm_minimum_bytes_per_launch": n * call_minimum_bytes(S, B, P, kb),
                          "frac_of_peak_by_hbm_minimum": n * call_minimum_bytes(S, B, P, kb) / (dom_ms * 1e-3) / 1e9 / peak,
                          "note": "achieved = SURVEY.md 8(d) bytes per stream per block x streams x blocks of one launch / its duration. A launch "
                                  "that walks k blocks tile-major re-reads a tile's FDL rows from L2, so DRAM `traffic` is below the algorithmic "
-                                 "bytes and `frac` can pass 1; hbm_minimum = the history read once + k new slots + input + output"},
+                                 "bytes and `frac` can pass 1; hbm_minimum = the history read once + k new slots + input + output. "
+                                 "fdl_rows: speakers that share a filter pair (FC and LFE) share one delay line, so the kernel keeps 7 rows "
+                                 "per 7.1 stream where the formula counts 8; frac_counting_shared_rows uses 8*rows*B*P for the FDL term"},
             "step_roofline": {"algorithmic_bytes_per_step": step_bytes, "achieved": step_bytes / (step_ms * 1e-3) / 1e9,
                               "frac": step_bytes / (step_ms * 1e-3) / 1e9 / peak, "kernels_ms": kernels_ms},
             "latency_ms": {"p50": per_step[len(per_step) // 2], "p99": per_step[min(len(per_step) - 1, int(0.99 * len(per_step)))],

@@ -177,6 +177,10 @@ AW_API int aw_bank_create_ex(int device, const float *pcm, int channels, int fra
 /* Convenience: load -> layout -> HeSuVi map -> bank, i.e. activatePreset(preset, targetSampleRate, inputLayout). */
 AW_API int aw_bank_create_from_wav(int device, const aw_wav *wav, double dst_rate, int layout, int block, aw_bank **out);
 AW_API int aw_bank_info(const aw_bank *bank, int *n_speakers, int *block, int *partitions, int *taps);
+/* Distinct (left, right) channel pairs among the bank's speakers = frequency-domain delay lines the block kernel keeps per stream.
+ * Speakers that share a pair — FC and LFE in both HeSuVi maps (VirtualSpeaker.swift:235-236, 281-283) — are summed before the
+ * forward transform and filtered once (linearity); 7 for 7.1, 5 for 5.1, 2 for stereo. */
+AW_API int aw_bank_rows(const aw_bank *bank);
 /* Copies the bank to the host as [speaker][partition][bin]{L.re, L.im, R.re, R.im}; bin 0 = DC; nyquist[speaker][partition]{L,R}. */
 AW_API int aw_bank_read(const aw_bank *bank, float *spectrum, float *nyquist);
 AW_API void aw_bank_destroy(aw_bank *bank);

@@ -428,3 +428,29 @@ def test_short_responses_with_many_blocks_per_call(aw, hrtf_path):
             assert np.abs(y[i] - ref).max() <= MAX_ABS, (taps, block, per_call_blocks, i)
         for i in range(9, n):
             assert np.array_equal(y[i], y[i % 9]), (taps, block, i)
+
+
+def test_speakers_sharing_a_filter_pair_share_one_delay_line(aw, hrtf_path):
+    """FC and LFE use the same HRIR pair in the HeSuVi maps (VirtualSpeaker.swift:281-283): the block kernel adds the two input
+    channels before the forward transform and keeps one frequency-domain delay line for both (conv(a,h) + conv(b,h) =
+    conv(a+b,h)).  Same samples as one delay line per speaker up to float32 rounding, both within the oracle bound, for single- and
+    multi-block calls (ragged calls, where the overlap buffer holds the summed block, are compared with the reference adapter
+    sample by sample in test_arbitrary_frame_counts_follow_the_reference_adapter)."""
+    wav = aw.WAVLoader.load(hrtf_path("RoomSH1.0"))
+    for layout, S, rows in (("surround71", 8, 7), ("surround51", 6, 5), ("stereo", 2, 2)):
+        assert aw.HRIRBank.from_wav(wav, FS, getattr(aw.InputLayout, layout)(), 256).rows == rows
+    h = oracle.hrir_matrix(oracle.load_wav(hrtf_path("RoomSH1.0")), FS, oracle.InputLayout.surround71)
+    for block, n, per_call in ((256, 37, 1024), (64, 150, 640), (1024, 9, 1024)):
+        bank = aw.HRIRBank.from_wav(wav, FS, aw.InputLayout.surround71(), block)
+        blocks = 24
+        xu, merged, plan = _render_twins(aw, bank, n, 8, block, blocks=blocks, unique=4, per_call=per_call, pcm_lr=None)
+        _, separate, _ = _render_twins(aw, bank, n, 8, block, blocks=blocks, unique=4, per_call=per_call, pcm_lr=None,
+                                       env={"AW_KP_MERGE_ROWS": "0"})
+        assert plan["kernels"][0].startswith("k_persistent<")
+        assert not np.array_equal(merged, separate) and np.abs(merged - separate).max() <= 2e-6
+        for y in (merged, separate):
+            for i in range(4):
+                ref = oracle.direct_conv_f64(xu[i], h)
+                assert np.abs(y[i] - ref).max() <= MAX_ABS and snr_db(ref, y[i]) >= SNR_DB
+            for i in range(4, n):
+                assert np.array_equal(y[i], y[i % 4])
