@@ -99,6 +99,8 @@ struct aw_bank {
     // speaker (literal-stereo engines, AW_KP_MERGE_ROWS=0)
     int R = 0;
     KpRowTable *d_rows = nullptr;   // [2]
+    float4 *d_bank_rows = nullptr;  // filter rows of the R distinct pairs, [R][P][2 planes][B/2] (== d_bank when R == S)
+    float *d_ny_rows = nullptr;     // [R][P][2]
 };
 
 namespace {
@@ -539,8 +541,9 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
                 k.head = seg.head;
                 k.tile0 = 0;
                 k.n_big = 0;
-                k.bank = seg.bank->d_bank;
-                k.bank_ny = seg.bank->d_ny;
+                const bool compact = merged && seg.bank->d_bank_rows != nullptr;   // (R == S: the rows are the speakers)
+                k.bank = compact ? seg.bank->d_bank_rows : seg.bank->d_bank;
+                k.bank_ny = compact ? seg.bank->d_ny_rows : seg.bank->d_ny;
             }
             if (n == 0) break;
             const bool prof = e->profOn && e->profUsed + 4 <= e->profEvents.size();
@@ -580,7 +583,13 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         BlockGeom g;
         g.first_stream = seg.first;
         g.n_streams = seg.count;
-        g.S = literal ? std::min(b->S, 2) : b->S;
+        const bool merged = e->kpMergeRows && !literal && b->d_rows != nullptr && b->R > 0;
+        const bool compact = merged && b->d_bank_rows != nullptr;
+        const float4 *bank_rows = compact ? b->d_bank_rows : b->d_bank;
+        const float *ny_rows = compact ? b->d_ny_rows : b->d_ny;
+        g.S = literal ? std::min(b->S, 2) : (merged ? b->R : b->S);
+        g.rows = merged ? b->d_rows : nullptr;
+        g.prev_is_rows = prev.ptr == e->d_overlap ? 1 : 0;
         g.Se = e->S;
         g.B = e->B;
         g.log2m = e->log2m;
@@ -593,15 +602,15 @@ int process_block(aw_engine *e, StridedIn cur, StridedIn prev, bool save_overlap
         if (prof) { e->profUsed += 4; cudaEventRecord(ev[0], e->stream); }
         if (e->fusedTile > 0) {
             // K2 + K3 + K4 in one kernel; events 0..1 bracket it, 1..3 collapse to zero-length intervals
-            AW_LAUNCH(e, launch_fused(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, b->d_bank, b->d_ny, out,
+            AW_LAUNCH(e, launch_fused(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, bank_rows, ny_rows, out,
                                       e->d_tw, e->fusedTile, st));
             if (prof) { cudaEventRecord(ev[1], e->stream); cudaEventRecord(ev[2], e->stream); cudaEventRecord(ev[3], e->stream); }
         } else {
             AW_LAUNCH(e, launch_input_rfft(g, cur, prev, save_overlap ? e->d_overlap : nullptr, e->d_fdl, e->d_fdl_ny, e->d_tw, st));
             if (prof) cudaEventRecord(ev[1], e->stream);
-            AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, b->d_bank, e->d_acc, e->macTile, st));
+            AW_LAUNCH(e, launch_fdl_cmac(g, e->d_fdl, bank_rows, e->d_acc, e->macTile, st));
             if (prof) cudaEventRecord(ev[2], e->stream);
-            AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, b->d_ny, out, e->d_tw, st));
+            AW_LAUNCH(e, launch_irfft_out(g, e->d_acc, e->d_fdl_ny, ny_rows, out, e->d_tw, st));
             if (prof) cudaEventRecord(ev[3], e->stream);
         }
     }
@@ -1054,6 +1063,7 @@ extern "C" int aw_bank_create_ex(int device, const float *pcm, int channels, int
                                                      : launch_resample_vgenp(d_ir, S * 2, frames, (float)(src_rate / dst_rate), d_rs, taps, 0);
         d_src = d_rs;
     }
+    int row_rep[kKpMaxRows] = {};
     if (e == cudaSuccess && S <= kKpMaxRows) {
         KpRowTable t[2];
         memset(t, -1, sizeof(t));
@@ -1069,6 +1079,7 @@ extern "C" int aw_bank_create_ex(int device, const float *pcm, int channels, int
             t[1].src[sp][0] = (signed char)sp;
         }
         b->R = rows;
+        for (int k = 0; k < rows; ++k) { row_rep[k] = t[0].spk[k]; t[0].spk[k] = (signed char)k; }   // rows index the compacted bank below
         e = cudaMalloc(&b->d_rows, sizeof(t));
         if (e == cudaSuccess) e = cudaMemcpy(b->d_rows, t, sizeof(t), cudaMemcpyHostToDevice);
     }
@@ -1076,10 +1087,20 @@ extern "C" int aw_bank_create_ex(int device, const float *pcm, int channels, int
     if (e == cudaSuccess) e = cudaMalloc(&b->d_ny, sizeof(float) * (size_t)S * b->P * 2);
     if (e == cudaSuccess) e = launch_bank_build(d_src, S, taps, block, log2m, b->P, b->d_bank, b->d_ny, tw, 0);
     if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e == cudaSuccess && b->R > 0 && b->R < S) {
+        // the filter rows of the distinct pairs, contiguous in row order: what the kernels walk when rows are shared
+        const size_t row_f4 = (size_t)b->P * block, row_ny = (size_t)b->P * 2;
+        e = cudaMalloc(&b->d_bank_rows, sizeof(float4) * row_f4 * b->R);
+        if (e == cudaSuccess) e = cudaMalloc(&b->d_ny_rows, sizeof(float) * row_ny * b->R);
+        for (int k = 0; k < b->R && e == cudaSuccess; ++k) {
+            e = cudaMemcpy(b->d_bank_rows + k * row_f4, b->d_bank + row_rep[k] * row_f4, sizeof(float4) * row_f4, cudaMemcpyDeviceToDevice);
+            if (e == cudaSuccess) e = cudaMemcpy(b->d_ny_rows + k * row_ny, b->d_ny + row_rep[k] * row_ny, sizeof(float) * row_ny, cudaMemcpyDeviceToDevice);
+        }
+    }
     cudaFree(d_ir);
     cudaFree(d_rs);
     if (e != cudaSuccess) {
-        cudaFree(b->d_bank); cudaFree(b->d_ny); cudaFree(b->d_rows);
+        cudaFree(b->d_bank); cudaFree(b->d_ny); cudaFree(b->d_rows); cudaFree(b->d_bank_rows); cudaFree(b->d_ny_rows);
         delete b;
         return set_error(e == cudaErrorMemoryAllocation ? AW_ERR_OUT_OF_MEMORY : AW_ERR_CUDA, std::string("aw_bank_create: ") + cudaGetErrorString(e));
     }
@@ -1133,6 +1154,8 @@ extern "C" void aw_bank_destroy(aw_bank *bank)
     cudaFree(bank->d_bank);
     cudaFree(bank->d_ny);
     cudaFree(bank->d_rows);
+    cudaFree(bank->d_bank_rows);
+    cudaFree(bank->d_ny_rows);
     delete bank;
 }
 

@@ -101,6 +101,20 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// 8-byte load of data that is read once (frame operands, accumulators): does not allocate in L1, which K2 / K4 keep for the
+// twiddle tables they read from global memory
+__device__ __forceinline__ float2 ld_once2(const float *p)
+{
+    float2 v;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
@@ -265,6 +279,75 @@ __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float
     group_sync<LOG2M>(gb);
 }
 
+// The input channels FDL row `s` sums (c[0] is always one; -1 = no more): read once per frame, so that the operand loads below do
+// not each wait for a table lookup.
+struct RowSources { int c[kKpMaxRowSources]; };
+__device__ __forceinline__ RowSources row_sources(const BlockGeom &g, int s)
+{
+    RowSources r;
+    if (g.rows) {
+        const char4 v = *reinterpret_cast<const char4 *>(g.rows->src[s]);
+        r.c[0] = v.x; r.c[1] = v.y; r.c[2] = v.z; r.c[3] = v.w;
+    } else {
+        r.c[0] = s; r.c[1] = r.c[2] = r.c[3] = -1;
+    }
+    return r;
+}
+static_assert(kKpMaxRowSources == 4, "row_sources reads the four sources of a row as one char4");
+
+// Operand i of the packed overlap-save frame [previous block | current block] of FDL row `s` of one stream (K2, KF): a row sums
+// the input channels that share its filter pair; the overlap buffer holds the previous block already summed (prev_is_rows), the
+// caller's input does not.
+template <int M>
+__device__ __forceinline__ float2 frame_operand(const BlockGeom &g, const RowSources &rs, const StridedIn &prev, const StridedIn &cur, int stream,
+                                                int s, int i)
+{
+    float2 v;
+    if (i < M / 2) {
+        v = ld_once2(prev.ptr + stream * prev.ss + (g.prev_is_rows ? s : rs.c[0]) * prev.cs + 2 * i);
+        if (!g.prev_is_rows) {
+#pragma unroll
+            for (int q = 1; q < kKpMaxRowSources; ++q)
+                if (rs.c[q] >= 0) {
+                    const float2 x = ld_once2(prev.ptr + stream * prev.ss + rs.c[q] * prev.cs + 2 * i);
+                    v.x += x.x; v.y += x.y;
+                }
+        }
+        return v;
+    }
+    const int j = 2 * (i - M / 2);
+    v = ld_once2(cur.ptr + stream * cur.ss + rs.c[0] * cur.cs + j);
+#pragma unroll
+    for (int q = 1; q < kKpMaxRowSources; ++q)
+        if (rs.c[q] >= 0) {
+            const float2 x = ld_once2(cur.ptr + stream * cur.ss + rs.c[q] * cur.cs + j);
+            v.x += x.x; v.y += x.y;
+        }
+    return v;
+}
+
+// The pass-0 operands of thread t for that frame (v[e] = z[load_index<0>(t, e)]), all loads first; then inputOverlapBuffer <- the
+// (summed) current block (ConvolutionEngine.swift:243) when `ov` is given: the overlap buffer may be `prev` itself, and a store
+// between the loads would make each of them wait for the one before.
+template <int LOG2M>
+__device__ __forceinline__ void fetch_frame(const BlockGeom &g, const StridedIn &prev, const StridedIn &cur, int stream, int s, float *ov, int t,
+                                            bool active, float2 (&v)[RegFft<LOG2M>::E])
+{
+    using F = RegFft<LOG2M>;
+    constexpr int M = F::M;
+    const RowSources rs = row_sources(g, s);
+#pragma unroll
+    for (int e = 0; e < F::E; ++e)
+        v[e] = active ? frame_operand<M>(g, rs, prev, cur, stream, s, F::template load_index<0>(t, e)) : make_float2(0.f, 0.f);
+    if (active && ov) {
+#pragma unroll
+        for (int e = 0; e < F::E; ++e) {
+            const int i = F::template load_index<0>(t, e);
+            if (i >= M / 2) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v[e];
+        }
+    }
+}
+
 __device__ __forceinline__ float group_sum(float v, int width)   // deterministic butterfly sum over `width` (<= 32) lanes
 {
     for (int o = width >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -274,9 +357,10 @@ __device__ __forceinline__ float group_sum(float v, int width)   // deterministi
 // Nyquist product sum for one (stream, ear): sum_{s,p} fdl_ny[stream][s][(head+p)%P] * bank_ny[s][p][ear], computed by
 // the G threads of a transform.  part_s: G floats of scratch for this transform.  Result valid in every thread after
 // the two barriers inside.
+// Thread t's share of that sum (partitions t, t + G, ...).
 template <int G>
-__device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fdl_ny, const float *bank_ny, int stream, int ear,
-                                             bool active, int t, float *part_s, GroupBar gb = GroupBar{0, 0})
+__device__ __forceinline__ float nyquist_partial(const BlockGeom &g, const float *fdl_ny, const float *bank_ny, int stream, int ear, bool active,
+                                                 int t)
 {
     float sum = 0.f;
     const int Pm = g.Pm > 0 ? g.Pm : g.P;
@@ -302,6 +386,22 @@ __device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fd
             }
         }
     }
+    return sum;
+}
+// The sum of the G partial sums in part_s[0..G), in the order nyquist_sum adds them; call with the threads t < 32 of the transform
+// (G > 32) after a barrier that follows the stores to part_s.  Result in each of them.
+template <int G>
+__device__ __forceinline__ float nyquist_reduce_warp0(const float *part_s, int t)
+{
+    float acc = 0.f;
+    for (int i = t; i < G; i += 32) acc += part_s[i];
+    return group_sum(acc, 32);
+}
+template <int G>
+__device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fdl_ny, const float *bank_ny, int stream, int ear,
+                                             bool active, int t, float *part_s, GroupBar gb = GroupBar{0, 0})
+{
+    const float sum = nyquist_partial<G>(g, fdl_ny, bank_ny, stream, ear, active, t);
     if constexpr (G <= 32) {
         return group_sum(sum, G);
     } else {
@@ -309,10 +409,7 @@ __device__ __forceinline__ float nyquist_sum(const BlockGeom &g, const float *fd
         part_s[t] = sum;
         sync();
         float acc = 0.f;
-        if (t < 32) {
-            for (int i = t; i < G; i += 32) acc += part_s[i];
-            acc = group_sum(acc, 32);
-        }
+        if (t < 32) acc = nyquist_reduce_warp0<G>(part_s, t);
         sync();               // everyone has read part_s[.] before slot 0 is overwritten
         if (t == 0) part_s[0] = acc;
         sync();

@@ -12,6 +12,20 @@
 // a CTA runs NF transforms side by side.  In the fused kernel THREADS = B/2 (one bin pair per thread in the MAC
 // phase) which makes NF = 8 for every supported B.
 #include "aw_fft_blocks.cuh"
+#include <cstdlib>
+
+// How K2 / K4 overlap the fetch of their next frame with the transform of the current one (block sizes where a CTA loops, B >= 2048):
+// 0 = not at all; 1 = prefetch.global.L2 of the next frame's lines; 2 = K2 only: pass-0 operands of the next frame in registers
+// (measured slower: the registers cost a resident CTA).
+#ifndef AW_K2_PIPE
+#define AW_K2_PIPE 1
+#endif
+#ifndef AW_SA_RESIDENT_THREADS
+#define AW_SA_RESIDENT_THREADS 768
+#endif
+#ifndef AW_K4_PIPE
+#define AW_K4_PIPE 1
+#endif
 
 namespace aw {
 
@@ -28,7 +42,31 @@ struct Geo {
     // transform buffers and 3x as many CTAs fit on an SM at B = 4096
     static constexpr size_t k1_smem = (size_t)(M + SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
     static constexpr size_t sa_smem = (size_t)(SA_NF * PS) * sizeof(float2) + (size_t)SA_THREADS * sizeof(float);
+    // from B = 2048 a CTA of K2/K4 loops over several frames (sa_grid): it fetches the next frame while it transforms this one
+    static constexpr bool LOOPS = LOG2M >= 11;
+    // resident CTAs of K2 / K4 the register budget is held to (80 registers: 768 threads)
+    static constexpr int MIN_CTAS = AW_SA_RESIDENT_THREADS / SA_THREADS > 0 ? AW_SA_RESIDENT_THREADS / SA_THREADS : 1;
+    static constexpr size_t k4_smem = sa_smem;
 };
+
+// the lines of the operands of `job` of K2 -> L2 (the loads of the next round then wait for L2, not DRAM)
+template <int LOG2M>
+__device__ __forceinline__ void k2_prefetch(const BlockGeom &g, const StridedIn &prev, const StridedIn &cur, int job, int jobs, int t)
+{
+    constexpr int M = 1 << LOG2M, G = RegFft<LOG2M>::G, LINES = M / 32;   // 128-byte lines in one block of M floats
+    if (job >= jobs) return;
+    const int ls = job / g.S, s = job - ls * g.S, stream = g.first_stream + ls;
+    const RowSources rs = row_sources(g, s);
+    for (int line = t; line < 2 * LINES; line += G) {
+        const bool second = line >= LINES;
+        const int off = (second ? line - LINES : line) * 32;
+        if (!second && g.prev_is_rows) { prefetch_l2(prev.ptr + stream * prev.ss + s * prev.cs + off); continue; }
+        const StridedIn &in = second ? cur : prev;
+#pragma unroll
+        for (int q = 0; q < kKpMaxRowSources; ++q)
+            if (rs.c[q] >= 0) prefetch_l2(in.ptr + stream * in.ss + rs.c[q] * in.cs + off);
+    }
+}
 
 // ------------------------------------------------------------------------------------------------
 // K2  input_rfft
@@ -43,7 +81,7 @@ struct InputRfftArgs {
 };
 
 template <int LOG2M>
-__global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_input_rfft(const InputRfftArgs a)
+__global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS, Geo<LOG2M>::MIN_CTAS) k_input_rfft(const InputRfftArgs a)
 {
     using Gm = Geo<LOG2M>;
     constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
@@ -52,27 +90,40 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_input_rfft(const Inp
     const float2 *tw = a.tw + M;          // the plan's per-pass twiddle tables (global memory, read through L1)
     const int tid = threadIdx.x, f = tid / G, t = tid % G;
     const int jobs = a.g.n_streams * a.g.S;
+    using F = RegFft<LOG2M>;
+    // pass-0 operands of `job`: frame = [previous block | current block] (:237-248); inputOverlapBuffer <- current block (:243)
+    auto fetch = [&](int job, float2 (&v)[F::E]) {
+        const bool active = job < jobs;
+        const int ls = active ? job / a.g.S : 0, s = active ? job - ls * a.g.S : 0;
+        const int stream = a.g.first_stream + ls;
+        float *ov = a.overlap_save ? a.overlap_save + ((size_t)stream * a.g.Se + s) * M : nullptr;
+        fetch_frame<LOG2M>(a.g, a.prev, a.cur, stream, s, ov, t, active, v);
+    };
+    float2 v[F::E];
+    if constexpr (Gm::LOOPS && AW_K2_PIPE == 2) fetch(blockIdx.x * NF + f, v);
     for (int base = blockIdx.x * NF; base < jobs; base += gridDim.x * NF) {   // uniform trip count: barriers inside
         const int job = base + f;
         const bool active = job < jobs;
         const int ls = active ? job / a.g.S : 0, s = active ? job - ls * a.g.S : 0;
         const int stream = a.g.first_stream + ls;
-        const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
-        const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
-        float *ov = a.overlap_save ? a.overlap_save + ((size_t)stream * a.g.Se + s) * M : nullptr;
         const size_t row = ((size_t)stream * a.g.Se + s) * a.g.P_cap + a.g.head;
         float2 *dst = a.fdl + row * M;
         float *dst_ny = a.fdl_ny + row;
-        forward_frame<LOG2M, true>(
-            bufs + (size_t)f * Gm::PS, tw, t, active,
-            [&](int i, int) -> float2 {   // frame = [previous block | current block]  (:237-248)
-                if (i < M / 2) return *reinterpret_cast<const float2 *>(prev + 2 * i);
-                const float2 v = *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2));
-                if (ov) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v;   // inputOverlapBuffer <- current block (:243);
-                return v;                                                          // same thread read this address as `prev`
-            },
+        float2 nv[F::E];
+        if constexpr (Gm::LOOPS && AW_K2_PIPE == 2) {
+            fetch(job + gridDim.x * NF, nv);               // in flight while this frame is transformed
+        } else {
+            if constexpr (Gm::LOOPS && AW_K2_PIPE == 1) k2_prefetch<LOG2M>(a.g, a.prev, a.cur, job + gridDim.x * NF, jobs, t);
+            fetch(job, v);
+        }
+        forward_frame_regs<LOG2M, true>(
+            bufs + (size_t)f * Gm::PS, tw, t, active, v,
             [&](int k, float2 x) { dst[k] = x; },       // FDL[head] <- spectrum (:256-264)
             [&](float ny) { *dst_ny = ny; });
+        if constexpr (Gm::LOOPS && AW_K2_PIPE == 2) {
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) v[e] = nv[e];
+        }
     }
 }
 
@@ -139,7 +190,7 @@ struct IrfftArgs {
 
 
 template <int LOG2M>
-__global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const IrfftArgs a)
+__global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS, Geo<LOG2M>::MIN_CTAS) k_irfft_out(const IrfftArgs a)
 {
     using Gm = Geo<LOG2M>;
     constexpr int M = Gm::M, G = Gm::G, NF = Gm::SA_NF;
@@ -154,13 +205,25 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS) k_irfft_out(const Irff
         const int job = base + f;
         const bool active = job < jobs;
         const int stream = a.g.first_stream + (active ? job >> 1 : 0), ear = job & 1;
-        __syncthreads();                  // the previous round is done with buf
+        const float ny_part = nyquist_partial<G>(a.g, a.fdl_ny, a.bank_ny, stream, ear, active, t);   // in flight with the copy below
+        __syncthreads();                  // the previous round is done with buf and part
+        if constexpr (Gm::LOOPS && AW_K4_PIPE == 1) {
+            const int next = job + gridDim.x * NF;
+            if (next < jobs) {
+                const float2 *src = a.acc + ((size_t)(a.g.first_stream + (next >> 1)) * 2 + (next & 1)) * M;
+                for (int line = t; line < M / 16; line += G) prefetch_l2(src + line * 16);
+            }
+        }
         if (active) {
             const float2 *src = a.acc + ((size_t)stream * 2 + ear) * M;
-            for (int k = t; k < M; k += G) buf[pad16(k)] = src[k];
+            for (int k = t; k < M; k += G) buf[pad16(k)] = ld_once2(reinterpret_cast<const float *>(src + k));
         }
+        if constexpr (G > 32) part[(size_t)f * G + t] = ny_part;
         __syncthreads();
-        const float ny = nyquist_sum<G>(a.g, a.fdl_ny, a.bank_ny, stream, ear, active, t, part + (size_t)f * G);
+        // the Nyquist sum, added up in nyquist_sum's order; only thread 0 of a transform uses it (bin 0 of the inverse split)
+        float ny = 0.f;
+        if constexpr (G <= 32) ny = group_sum(ny_part, G);
+        else if (t < 32) ny = nyquist_reduce_warp0<G>(part + (size_t)f * G, t);
         float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
         inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
     }
@@ -337,20 +400,14 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
         const int ls = idx / g.S, s = idx - ls * g.S;
         const bool active = idx < nfft && ls < nvalid;
         const int stream = s0 + (active ? ls : 0);
-        const float *prev = a.prev.ptr + stream * a.prev.ss + s * a.prev.cs;
-        const float *cur = a.cur.ptr + stream * a.cur.ss + s * a.cur.cs;
         float *ov = a.overlap_save ? a.overlap_save + ((size_t)stream * g.Se + s) * M : nullptr;
         const size_t row = ((size_t)stream * g.Se + s) * g.P_cap + g.head;
         float2 *dst = a.fdl + row * M;
         float *dst_ny = a.fdl_ny + row;
-        forward_frame<LOG2M>(
-            bufs + (size_t)f * FG::PS, tw, t, active,
-            [&](int i, int) -> float2 {
-                if (i < M / 2) return *reinterpret_cast<const float2 *>(prev + 2 * i);
-                const float2 v = *reinterpret_cast<const float2 *>(cur + 2 * (i - M / 2));
-                if (ov) *reinterpret_cast<float2 *>(ov + 2 * (i - M / 2)) = v;
-                return v;
-            },
+        float2 v[RegFft<LOG2M>::E];
+        fetch_frame<LOG2M>(g, a.prev, a.cur, stream, s, ov, t, active, v);
+        forward_frame_regs<LOG2M>(
+            bufs + (size_t)f * FG::PS, tw, t, active, v,
             [&](int k, float2 x) { dst[k] = x; },
             [&](float ny) { *dst_ny = ny; });
     }
@@ -407,16 +464,21 @@ __global__ void __launch_bounds__(FusedGeo<LOG2M>::THREADS, MINB) k_fused(const 
 // grid of the stand-alone transform kernels: every CTA loops over its share of the frames, so no more CTAs than can be resident
 // (227 KB of shared memory per SM, 148 SMs) — the twiddle tables are then built once per resident CTA instead of once per frame
 template <int LOG2M>
-static int sa_grid(int jobs)
+static int sa_grid(int jobs, size_t smem, const void *kernel, int which)
 {
     const int ctas = (jobs + Geo<LOG2M>::SA_NF - 1) / Geo<LOG2M>::SA_NF;
     if (LOG2M <= 10) return ctas;   // measured: up to B = 1024 one frame group per CTA is faster (the CTA scheduler overlaps them)
-    int per_sm = (int)((227 * 1024) / (Geo<LOG2M>::sa_smem + 1024));
-    const int by_threads = 2048 / Geo<LOG2M>::SA_THREADS;
-    if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm < 1) per_sm = 1;
-    const int resident = 148 * per_sm;
-    return ctas < resident ? ctas : resident;
+    static int resident[2] = {0, 0};   // [K2, K4] of this block size: SMs x the CTAs of the kernel that fit on one
+    int &r = resident[which];
+    if (r == 0) {
+        int per_sm = 0, dev = 0, sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Geo<LOG2M>::SA_THREADS, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        int waves = 2;   // measured at B = 4096: two CTAs per resident slot, each looping over half as many frames, hide the tail better
+        if (const char *v = getenv("AW_SA_WAVES")) waves = atoi(v) > 0 ? atoi(v) : 1;
+        r = sms * per_sm * waves;
+    }
+    return ctas < r ? ctas : r;
 }
 
 cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev, float *overlap_save, float2 *fdl,
@@ -425,7 +487,7 @@ cudaError_t launch_input_rfft(const BlockGeom &g, StridedIn cur, StridedIn prev,
     const int jobs = g.n_streams * g.S;
     if (jobs <= 0) return cudaSuccess;
     InputRfftArgs a{g, cur, prev, overlap_save, fdl, fdl_ny, tw};
-#define CALL(L) k_input_rfft<L><<<sa_grid<L>(jobs), Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+#define CALL(L) k_input_rfft<L><<<sa_grid<L>(jobs, Geo<L>::sa_smem, (const void *)k_input_rfft<L>, 0), Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
     AW_LOG2M_SWITCH(g.log2m, CALL)
 #undef CALL
     return cudaGetLastError();
@@ -437,7 +499,7 @@ cudaError_t launch_irfft_out(const BlockGeom &g, const float2 *acc, const float 
     const int jobs = g.n_streams * 2;
     if (jobs <= 0) return cudaSuccess;
     IrfftArgs a{g, acc, fdl_ny, bank_ny, out, tw};
-#define CALL(L) k_irfft_out<L><<<sa_grid<L>(jobs), Geo<L>::SA_THREADS, Geo<L>::sa_smem, st>>>(a)
+#define CALL(L) k_irfft_out<L><<<sa_grid<L>(jobs, Geo<L>::k4_smem, (const void *)k_irfft_out<L>, 1), Geo<L>::SA_THREADS, Geo<L>::k4_smem, st>>>(a)
     AW_LOG2M_SWITCH(g.log2m, CALL)
 #undef CALL
     return cudaGetLastError();
@@ -585,7 +647,9 @@ cudaError_t configure_kernels(int log2m)
     do {                                                                                                                     \
         if (Geo<L>::sa_smem > 48 * 1024) {                                                                                   \
             if ((e = cudaFuncSetAttribute(k_input_rfft<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e; \
-            if ((e = cudaFuncSetAttribute(k_irfft_out<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::sa_smem)) != cudaSuccess) return e;  \
+        }                                                                                                                    \
+        if (Geo<L>::k4_smem > 48 * 1024) {                                                                                   \
+            if ((e = cudaFuncSetAttribute(k_irfft_out<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::k4_smem)) != cudaSuccess) return e;  \
         }                                                                                                                    \
         if (Geo<L>::k1_smem > 48 * 1024) {                                                                                   \
             if ((e = cudaFuncSetAttribute(k_bank_build<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Geo<L>::k1_smem)) != cudaSuccess) return e; \

@@ -9,7 +9,7 @@ namespace aw {
 struct BlockGeom {
     int first_stream;   // first stream of the segment
     int n_streams;      // streams in the segment
-    int S;              // renderers of the segment's bank (speakers convolved)
+    int S;              // FDL rows of the segment's bank (distinct renderers: speakers that share a filter pair share a row)
     int Se;             // speakers per stream the engine's state arrays are laid out for (S <= Se)
     int B;              // block size = complex bins per spectrum
     int log2m;          // log2(B)
@@ -17,6 +17,8 @@ struct BlockGeom {
     int Pm;             // ring modulus when it differs from P (KP keeps one spare slot, see KpSegment); 0 = P
     int P_cap;          // FDL slots allocated per (stream, speaker)
     int head;           // fdlIndex after the decrement for this block
+    int prev_is_rows;   // 1: the `prev` operand of the forward kernels is the engine's overlap buffer (one summed block per FDL row)
+    const struct KpRowTable *rows;   // which input channels an FDL row sums (KpRowTable); nullptr: row s = input channel s
 };
 
 struct StridedIn {      // planar input: ptr[stream*ss + channel*cs + i]

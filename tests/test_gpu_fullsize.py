@@ -454,3 +454,20 @@ def test_speakers_sharing_a_filter_pair_share_one_delay_line(aw, hrtf_path):
                 assert np.abs(y[i] - ref).max() <= MAX_ABS and snr_db(ref, y[i]) >= SNR_DB
             for i in range(4, n):
                 assert np.array_equal(y[i], y[i % 4])
+    # the other execution paths keep the same rows: the three-kernel path (the only one for B < 64 and B = 4096) and the one-launch
+    # fused kernel sum the channels of a row in their forward stage and walk the bank's compacted rows
+    for block, n, per_call, env, first in ((256, 21, 512, {"AW_FUSED_TILE": "0"}, "k_input_rfft<"), (256, 21, 768, {"AW_PERSISTENT": "0"}, "k_fused<"),
+                                           (32, 40, 96, {}, "k_input_rfft<"), (4096, 5, 4096, {}, "k_input_rfft<")):
+        bank = aw.HRIRBank.from_wav(wav, FS, aw.InputLayout.surround71(), block)
+        blocks = 12 if block < 4096 else 6
+        xu, merged, plan = _render_twins(aw, bank, n, 8, block, blocks=blocks, unique=4, per_call=per_call, pcm_lr=None, env=env)
+        _, separate, _ = _render_twins(aw, bank, n, 8, block, blocks=blocks, unique=4, per_call=per_call, pcm_lr=None,
+                                       env=dict(env, AW_KP_MERGE_ROWS="0"))
+        assert plan["kernels"][0].startswith(first), plan["kernels"]
+        assert not np.array_equal(merged, separate) and np.abs(merged - separate).max() <= 2e-6
+        for y in (merged, separate):
+            for i in range(4):
+                ref = oracle.direct_conv_f64(xu[i], h)
+                assert np.abs(y[i] - ref).max() <= MAX_ABS and snr_db(ref, y[i]) >= SNR_DB, (block, env, i)
+            for i in range(4, n):
+                assert np.array_equal(y[i], y[i % 4]), (block, env, i)

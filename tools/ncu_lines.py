@@ -36,12 +36,13 @@ for k in sorted({k[0] for k in agg}):
     for s, ins, f, ln, text in sorted(items, reverse=True)[:top]:
         print(f'{100.0*s/tot:6.2f}%  inst {100.0*ins/toti:5.2f}%  {f}:{ln}: {text.strip()[:110]}')
     # per source file: the transform code lives in aw_fft*.cuh, the producer / MAC roles in aw_persistent.cu (and the PTX wrappers
-    # and cmac2f of aw_fft_blocks.cuh lines < 120).  "FFT share" = warp-instructions issued by the transform code: with the
+    # and cmac2f of aw_fft_blocks.cuh lines < 123).  "FFT share" = warp-instructions issued by the transform code: with the
     # kernel's issue-slot utilisation (smsp__issue_active) it gives the SM throughput the FFT warps reach on their own.
     by_file = {}
     for s_, ins, f, ln, text in items:
-        role = 'transforms (aw_fft_reg.cuh, aw_fft.cuh, aw_fft_blocks.cuh >= line 120)' if (f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and ln >= 120)) else \
-               ('multiply-accumulate + PTX wrappers (aw_fft_blocks.cuh < line 120)' if f == 'aw_fft_blocks.cuh' else f)
+        role = 'transforms (aw_fft_reg.cuh, aw_fft.cuh, aw_fft_blocks.cuh lines 123-271)' if (f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and 123 <= ln < 272)) else \
+               ('frame operand loads (aw_fft_blocks.cuh >= line 272)' if (f == 'aw_fft_blocks.cuh' and ln >= 272) else
+                'multiply-accumulate + PTX wrappers (aw_fft_blocks.cuh < line 123)' if f == 'aw_fft_blocks.cuh' else f)
         a = by_file.setdefault(role, [0, 0])
         a[0] += s_; a[1] += ins
     for role, (s_, ins) in sorted(by_file.items(), key=lambda kv: -kv[1][1]):

@@ -9,8 +9,10 @@ rows = list(csv.reader(io.StringIO(out)))
 kernel = fname = hdr = None
 roles = {}
 def role_of(f, ln):
-    if f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and ln >= 120):
+    if f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and 123 <= ln < 272):
         return 'transforms'
+    if f == 'aw_fft_blocks.cuh' and ln >= 272:
+        return 'frame-operand-loads'
     if f == 'aw_fft_blocks.cuh':
         return 'mac+ptx-wrappers'
     if f.startswith('sm_'):
