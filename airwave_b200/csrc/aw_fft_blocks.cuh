@@ -162,14 +162,14 @@ __device__ __forceinline__ void group_sync(GroupBar gb = GroupBar{0, 0})
 
 // Passes [P, LAST] entirely in shared memory (in place); every thread of the transform's group must call it.
 // PT: `tw` is a per-pass twiddle table (RegFft::pt_entry layout) instead of the half-circle table.
-template <int LOG2M, int P, bool PT>
+template <int LOG2M, int P, int PT>
 __device__ __forceinline__ void pass_compute(float2 (&v)[RegFft<LOG2M>::E], const float2 *tw, int t)
 {
-    if constexpr (PT) RegFft<LOG2M>::template compute_pt<P>(v, tw, t);
+    if constexpr (PT != 0) RegFft<LOG2M>::template compute_pt<P, PT == 2>(v, tw, t);
     else RegFft<LOG2M>::template compute<P>(v, tw, t);
 }
 
-template <int LOG2M, int P, int LAST, bool PT = false>
+template <int LOG2M, int P, int LAST, int PT = 0>
 struct SmemPasses {
     __device__ __forceinline__ static void run(float2 *buf, const float2 *tw, int t, GroupBar gb = GroupBar{0, 0})
     {
@@ -190,7 +190,7 @@ struct SmemPasses {
 // k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
 // Body of the forward real FFT of one frame whose pass-0 operands are already in registers (v[e] = z[load_index<0>(t, e)]):
 // lets a caller fetch the next frame from global memory while this one is being transformed.
-template <int LOG2M, bool PT = false, class Emit, class EmitNy>
+template <int LOG2M, int PT = 0, class Emit, class EmitNy>
 __device__ __forceinline__ void forward_frame_regs(float2 *buf, const float2 *tw, int t, bool active, float2 (&v)[RegFft<LOG2M>::E],
                                                    Emit emit, EmitNy emit_ny, GroupBar gb = GroupBar{0, 0})
 {
@@ -223,7 +223,7 @@ __device__ __forceinline__ void forward_frame_regs(float2 *buf, const float2 *tw
 
 // Forward real FFT of one frame.  `load(i)` returns z[i] = x[2i] + i*x[2i+1] of the frame (i < M); `emit(k, X)` is called
 // by the owning threads for k = 0..M-1 with the packed spectrum 2*X[k] (k = 0: (2*DC, 0)) and `emit_ny(2*X[M])` once.
-template <int LOG2M, bool PT = false, class Load, class Emit, class EmitNy>
+template <int LOG2M, int PT = 0, class Load, class Emit, class EmitNy>
 __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int t, bool active, Load load, Emit emit, EmitNy emit_ny,
                                               GroupBar gb = GroupBar{0, 0})
 {
@@ -238,7 +238,7 @@ __device__ __forceinline__ void forward_frame(float2 *buf, const float2 *tw, int
 // `emit(i, x0, x1)` receives the time samples x[2i], x[2i+1] for i in [M/2, M) — the overlap-save "second half".
 // All threads of the CTA must call it (barriers); `active` masks the stores only.
 // SYNC_BEFORE_EMIT: barrier between the last pass's loads and `emit`, for callers whose emit overwrites `buf`.
-template <int LOG2M, bool SYNC_BEFORE_EMIT = false, bool PT = false, class Emit>
+template <int LOG2M, bool SYNC_BEFORE_EMIT = false, int PT = 0, class Emit>
 __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float2 *tw, int t, bool active, Emit emit,
                                               GroupBar gb = GroupBar{0, 0})
 {

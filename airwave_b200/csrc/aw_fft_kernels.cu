@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS, Geo<LOG2M>::MIN_CTAS) 
             if constexpr (Gm::LOOPS && AW_K2_PIPE == 1) k2_prefetch<LOG2M>(a.g, a.prev, a.cur, job + gridDim.x * NF, jobs, t);
             fetch(job, v);
         }
-        forward_frame_regs<LOG2M, true>(
+        forward_frame_regs<LOG2M, 2>(
             bufs + (size_t)f * Gm::PS, tw, t, active, v,
             [&](int k, float2 x) { dst[k] = x; },       // FDL[head] <- spectrum (:256-264)
             [&](float ny) { *dst_ny = ny; });
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS, Geo<LOG2M>::MIN_CTAS) 
         if constexpr (G <= 32) ny = group_sum(ny_part, G);
         else if (t < 32) ny = nyquist_reduce_warp0<G>(part + (size_t)f * G, t);
         float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
-        inverse_frame<LOG2M, false, true>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
+        inverse_frame<LOG2M, false, 2>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
     }
 }
 

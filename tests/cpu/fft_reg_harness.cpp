@@ -8,8 +8,9 @@
 
 using namespace awfft;
 
-// `pt`: use the per-pass twiddle tables (RegFft::pt_entry layout, compute_pt) instead of the half-circle table
-static bool g_use_pt = false;
+// `pt`: 1 = use the per-pass twiddle tables (RegFft::pt_entry layout, compute_pt) instead of the half-circle table;
+// 2 = the same tables, radix-16 twiddles as six reads and nine products (K2 / K4)
+static int g_use_pt = 0;
 
 template <int LOG2M, int P>
 struct RunPasses {
@@ -24,7 +25,8 @@ struct RunPasses {
         }
         for (int t = 0; t < F::G; ++t) {
             float2(&v)[F::E] = *reinterpret_cast<float2(*)[F::E]>(&regs[(size_t)t * F::E]);
-            if (g_use_pt) F::template compute_pt<(P < F::PASSES ? P : 0)>(v, tw, t);
+            if (g_use_pt == 2) F::template compute_pt<(P < F::PASSES ? P : 0), true>(v, tw, t);
+            else if (g_use_pt) F::template compute_pt<(P < F::PASSES ? P : 0)>(v, tw, t);
             else F::template compute<(P < F::PASSES ? P : 0)>(v, tw, t);
             PassRunner<LOG2M, (P < F::PASSES ? P : 0)>::store(buf.data(), v, t);
         }
@@ -51,7 +53,7 @@ static void fft_one(const float *in, float *out)
     for (int i = 0; i < M; ++i) { out[2 * i] = buf[pad16(i)].x; out[2 * i + 1] = buf[pad16(i)].y; }
 }
 
-extern "C" void harness_regfft_use_pt(int on) { g_use_pt = on != 0; }
+extern "C" void harness_regfft_use_pt(int mode) { g_use_pt = mode; }
 
 extern "C" int harness_regfft(const float *in, int log2m, float *out)
 {

@@ -65,6 +65,29 @@ def test_per_pass_twiddle_tables_give_bit_identical_transforms(regfft, log2m):
 
 
 @pytest.mark.parametrize("log2m", range(2, 14))
+def test_twiddle_products_stay_within_the_transform_tolerance(regfft, log2m):
+    """K2 / K4 read six twiddles per radix-16 pass and multiply for the other nine (compute_pt<P, true>): same tolerance against
+    numpy as the table-only transform, and bit-identical to it where no pass is a radix-16 pass with twiddles."""
+    M = 1 << log2m
+    rng = np.random.default_rng(300 + log2m)
+    inp = rng.uniform(-1, 1, (M, 2)).astype(np.float32)
+    a, b = np.zeros((M, 2), np.float32), np.zeros((M, 2), np.float32)
+    try:
+        regfft.harness_regfft_use_pt(1)
+        assert regfft.harness_regfft(inp.ctypes.data_as(FP), log2m, a.ctypes.data_as(FP)) == 0
+        regfft.harness_regfft_use_pt(2)
+        assert regfft.harness_regfft(inp.ctypes.data_as(FP), log2m, b.ctypes.data_as(FP)) == 0
+    finally:
+        regfft.harness_regfft_use_pt(0)
+    ref = np.fft.fft(inp[:, 0].astype(np.float64) + 1j * inp[:, 1].astype(np.float64))
+    assert np.abs((b[:, 0] + 1j * b[:, 1]) - ref).max() <= 4e-7 * np.abs(ref).max()
+    if log2m in (2, 3, 4, 5, 6, 7, 9, 10):       # pass plans without a twiddled radix-16 pass (aw_fft_reg.cuh pass_log2r)
+        assert np.array_equal(a, b)
+    else:
+        assert not np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("log2m", range(2, 14))
 def test_real_fft_split_steps_match_numpy_and_round_trip(stockham, log2m):
     M, nf = 1 << log2m, 3
     N = 2 * M
