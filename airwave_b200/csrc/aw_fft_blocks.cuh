@@ -279,6 +279,65 @@ __device__ __forceinline__ void inverse_frame(float2 *buf, float ny, const float
     group_sync<LOG2M>(gb);
 }
 
+// inverse_frame with the packed spectrum still in global memory (K4): the inverse split is applied on the way into the transform
+// buffer (one pass over shared memory and one barrier less than copying first).  `ny_after_barrier()` is called by every thread
+// after the first barrier and returns the Nyquist value in thread 0 of the transform, which owns bin 0 here and in pass 0.
+template <int LOG2M, int PT = 0, class Ny, class Emit>
+__device__ __forceinline__ void inverse_frame_global(float2 *buf, const float2 *src, const float2 *tw, int t, bool active, Ny ny_after_barrier,
+                                                     Emit emit, GroupBar gb = GroupBar{0, 0})
+{
+    using F = RegFft<LOG2M>;
+    constexpr int M = F::M, G = F::G;
+    constexpr int NP = (M / 2 + G) / G;            // bins k = t + n*G <= M/2 per thread, at most
+    if (active) {
+        float2 a[NP], b[NP];
+#pragma unroll
+        for (int n = 0; n < NP; ++n) {
+            const int k = t + n * G;
+            if (k <= M / 2) {
+                a[n] = ld_once2(reinterpret_cast<const float *>(src + k));
+                b[n] = k == 0 ? a[n] : ld_once2(reinterpret_cast<const float *>(src + (M - k)));
+            }
+        }
+#pragma unroll
+        for (int n = 0; n < NP; ++n) {
+            const int k = t + n * G;
+            if (k == 0) {
+                buf[0] = a[n];                     // (DC, -): combined with the Nyquist value below
+            } else if (k <= M / 2) {
+                const int j = M - k;
+                const float er = a[n].x + b[n].x, ei = a[n].y - b[n].y;
+                const float dr = a[n].x - b[n].x, di = a[n].y + b[n].y;
+                const float2 w = make_float2(tw[k].x, -tw[k].y);
+                const float tr = w.x * dr - w.y * di, ti = w.x * di + w.y * dr;
+                buf[pad16(k)] = make_float2(er - ti, -(ei + tr));
+                if (j != k) buf[pad16(j)] = make_float2(er + ti, -(-ei + tr));
+            }
+        }
+    }
+    group_sync<LOG2M>(gb);
+    const float ny = ny_after_barrier();
+    if (t == 0) {                                  // the same thread loads bin 0 in pass 0: no barrier needed
+        const float dc = buf[0].x;
+        buf[0] = make_float2(dc + ny, -(dc - ny));
+    }
+    SmemPasses<LOG2M, 0, F::PASSES - 2, PT>::run(buf, tw, t, gb);
+    {
+        constexpr int P = F::PASSES - 1;
+        float2 v[F::E];
+        smem_load<LOG2M, P>(buf, v, t);
+        pass_compute<LOG2M, P, PT>(v, tw, t);
+        if (active) {
+#pragma unroll
+            for (int e = 0; e < F::E; ++e) {
+                const int i = F::template store_index<P>(t, e);
+                if (i >= M / 2) emit(i - M / 2, v[e].x, -v[e].y);
+            }
+        }
+    }
+    group_sync<LOG2M>(gb);
+}
+
 // The input channels FDL row `s` sums (c[0] is always one; -1 = no more): read once per frame, so that the operand loads below do
 // not each wait for a table lookup.
 struct RowSources { int c[kKpMaxRowSources]; };

@@ -214,18 +214,16 @@ __global__ void __launch_bounds__(Geo<LOG2M>::SA_THREADS, Geo<LOG2M>::MIN_CTAS) 
                 for (int line = t; line < M / 16; line += G) prefetch_l2(src + line * 16);
             }
         }
-        if (active) {
-            const float2 *src = a.acc + ((size_t)stream * 2 + ear) * M;
-            for (int k = t; k < M; k += G) buf[pad16(k)] = ld_once2(reinterpret_cast<const float *>(src + k));
-        }
         if constexpr (G > 32) part[(size_t)f * G + t] = ny_part;
-        __syncthreads();
-        // the Nyquist sum, added up in nyquist_sum's order; only thread 0 of a transform uses it (bin 0 of the inverse split)
-        float ny = 0.f;
-        if constexpr (G <= 32) ny = group_sum(ny_part, G);
-        else if (t < 32) ny = nyquist_reduce_warp0<G>(part + (size_t)f * G, t);
         float *row = a.out.ptr + stream * a.out.ss + ear * a.out.cs;
-        inverse_frame<LOG2M, false, 2>(buf, ny, tw, t, active, [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
+        inverse_frame_global<LOG2M, 2>(
+            buf, a.acc + ((size_t)stream * 2 + ear) * M, tw, t, active,
+            // the Nyquist sum, added up in nyquist_sum's order; only thread 0 of a transform uses it (bin 0 of the inverse split)
+            [&]() -> float {
+                if constexpr (G <= 32) return group_sum(ny_part, G);
+                else return t < 32 ? nyquist_reduce_warp0<G>(part + (size_t)f * G, t) : 0.f;
+            },
+            [&](int i, float x0, float x1) { store_pair(a.out, row, 2 * i, x0, x1); });
     }
 }
 
