@@ -30,7 +30,7 @@ for name, skip in [("C2", 100), ("C4", 190)]:
         f.write("(40 consecutive launches inside the timed region; per-launch times under ncu are cold-cache and serialised: compare shares)\n")
         for k, v in agg.items():
             f.write(f"{k[:90]:90s} launches {len(v):3d}  mean {sum(v)/len(v):9.2f} us  share {100*sum(v)/tot:5.1f}%\n")
-workloads = ["C2", "C2k1", "C3", "C4", "C5-512", "C5-64", "C5-2048", "C4eq", "C5-4096_k2"]
+workloads = ["C2", "C2k1", "C3", "C4", "C5-512", "C5-64", "C5-2048", "C4eq", "C5-4096_k2", "C5-4096_k4"]
 with open(f"profiles/{R}_ncu_summary.txt", "w") as f:
     f.write("# ncu summaries (tools/ncu_summary.py + tools/ncu_lines.py over the .ncu-rep files of tools/profile_round.sh)\n"
             "# Captures: ncu --set full --clock-control none --import-source on -k regex:<kernel> -s 45 -c 1 python bench.py --workload <W> --steps 4 --warmup 41 --no-cpu --e2e-steps 3, one B200.\n"
@@ -43,8 +43,9 @@ with open(f"profiles/{R}_ncu_summary.txt", "w") as f:
         f.write("--- top source lines by warp-stall samples\n")
         f.write(subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "k_", "10"], capture_output=True, text=True).stdout)
 out = {}
-for w, kern in [("C2", "k_persistent<8,4>"), ("C2k1", "k_persistent<8,4>"), ("C3", "k_persistent<9,4>"), ("C4", "k_persistent<8,4>"), ("C5-512", "k_persistent<9,4>"), ("C5-64", "k_persistent<6,4>"), ("C5-2048", "k_persistent<11,2>")]:
-    raw = subprocess.run(["ncu", "-i", f"{REP}/{R}_full_{w}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+for w, kern in [("C2", "k_persistent<8,4>"), ("C2k1", "k_persistent<8,4>"), ("C3", "k_persistent<9,4>"), ("C4", "k_persistent<8,4>"), ("C5-512", "k_persistent<9,4>"), ("C5-64", "k_persistent<6,4>"), ("C5-2048", "k_persistent<11,2>"),
+                ("C5-4096", "k_input_rfft<12>")]:
+    raw = subprocess.run(["ncu", "-i", f"{REP}/{R}_full_{w if w != 'C5-4096' else 'C5-4096_k2'}.ncu-rep", "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     h, u, r = rows[0], rows[1], rows[2]
     def val(name):

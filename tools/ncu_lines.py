@@ -40,8 +40,8 @@ for k in sorted({k[0] for k in agg}):
     # kernel's issue-slot utilisation (smsp__issue_active) it gives the SM throughput the FFT warps reach on their own.
     by_file = {}
     for s_, ins, f, ln, text in items:
-        role = 'transforms (aw_fft_reg.cuh, aw_fft.cuh, aw_fft_blocks.cuh lines 123-271)' if (f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and 123 <= ln < 272)) else \
-               ('frame operand loads (aw_fft_blocks.cuh >= line 272)' if (f == 'aw_fft_blocks.cuh' and ln >= 272) else
+        role = 'transforms (aw_fft_reg.cuh, aw_fft.cuh, aw_fft_blocks.cuh lines 123-340)' if (f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and 123 <= ln < 341)) else \
+               ('frame operand loads, Nyquist sums (aw_fft_blocks.cuh >= line 341)' if (f == 'aw_fft_blocks.cuh' and ln >= 341) else
                 'multiply-accumulate + PTX wrappers (aw_fft_blocks.cuh < line 123)' if f == 'aw_fft_blocks.cuh' else f)
         a = by_file.setdefault(role, [0, 0])
         a[0] += s_; a[1] += ins

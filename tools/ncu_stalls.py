@@ -9,9 +9,9 @@ rows = list(csv.reader(io.StringIO(out)))
 kernel = fname = hdr = None
 roles = {}
 def role_of(f, ln):
-    if f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and 123 <= ln < 272):
+    if f in ('aw_fft_reg.cuh', 'aw_fft.cuh') or (f == 'aw_fft_blocks.cuh' and 123 <= ln < 341):
         return 'transforms'
-    if f == 'aw_fft_blocks.cuh' and ln >= 272:
+    if f == 'aw_fft_blocks.cuh' and ln >= 341:
         return 'frame-operand-loads'
     if f == 'aw_fft_blocks.cuh':
         return 'mac+ptx-wrappers'

@@ -16,6 +16,7 @@ done
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_persistent -s 45 -c 1 -o $REP/${R}_full_C2k1 -f python bench.py --workload C2 --blocks-per-call 1 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_C2k1.log 2>&1; echo "C2k1 rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_eq_systolic -s 45 -c 1 -o $REP/${R}_full_C4eq -f python bench.py --workload C4 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 --no-single-block > gpurun_out/ncu_C4eq.log 2>&1; echo "C4eq rc=$?"
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_input_rfft -s 45 -c 1 -o $REP/${R}_full_C5-4096_k2 -f python bench.py --workload C5-4096 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_k2.log 2>&1; echo "K2 rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_irfft_out -s 45 -c 1 -o $REP/${R}_full_C5-4096_k4 -f python bench.py --workload C5-4096 --steps 4 --warmup 41 --no-cpu --e2e-steps 3 > gpurun_out/ncu_k4.log 2>&1; echo "K4 rc=$?"
 # summarise on the box (ncu reads its own reports), keep the text + the C2 report
 AW_REP_DIR=$REP python tools/collect_profiles.py $R && cp profiles/${R}_* gpurun_out/ && cp $REP/${R}_full_C2.ncu-rep gpurun_out/ 2>/dev/null
 ls -la gpurun_out | tail -20

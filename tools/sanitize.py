@@ -17,7 +17,14 @@ for block, n, env in [(64, 9, {}), (128, 9, {}), (256, 21, {}), (512, 9, {}), (1
                       # round 2: bulk-copy fallback, block-major walk, one launch per block, staged copies instead of zero-copy,
                       # the reference's ring modulus
                       (256, 21, {"AW_KP_TENSOR_TMA": "0"}), (64, 37, {"AW_KP_TENSOR_TMA": "0"}), (128, 300, {"AW_KP_ORDER": "0"}),
-                      (256, 9, {"AW_KP_MULTIBLOCK": "0"}), (64, 9, {"AW_ZERO_COPY": "0"}), (512, 9, {"AW_KP_RING_EXTRA": "0"})]:
+                      (256, 9, {"AW_KP_MULTIBLOCK": "0"}), (64, 9, {"AW_ZERO_COPY": "0"}), (512, 9, {"AW_KP_RING_EXTRA": "0"}),
+                      # the stand-alone transforms: small blocks, CTAs that loop over frames (more frames than resident CTAs), one
+                      # delay line per speaker, the fused kernel with shared rows at another block size
+                      (32, 9, {}), (2048, 70, {"AW_FUSED_TILE": "0", "AW_SA_WAVES": "1"}), (4096, 3, {"AW_KP_MERGE_ROWS": "0"}),
+                      (512, 9, {"AW_PERSISTENT": "0"})]:
+    # AW_SANITIZE_ONLY=transforms: only the plans that run K2 / K4 / KF (what a change to those kernels needs re-checked)
+    if os.environ.get("AW_SANITIZE_ONLY") == "transforms" and not (block in (32, 4096) or "AW_FUSED_TILE" in env or "AW_PERSISTENT" in env):
+        continue
     os.environ.update(env)
     bank = aw.HRIRBank.from_wav(wav, FS, aw.InputLayout.surround71(), block)
     eng = aw.BinauralEngine(n, 8, block, FS, max_frames_per_call=min(4096, 2 * block))
