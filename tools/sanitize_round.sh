@@ -10,9 +10,9 @@ mkdir -p gpurun_out
   echo "# commit ${AW_GIT_SHA:-unknown}; library sha256 $(sha256sum airwave_b200/lib/libairwave_cuda.so | cut -c1-16); $(date -u +%FT%TZ)"
   for tool in memcheck synccheck initcheck; do
     echo; echo "## compute-sanitizer --tool $tool python tools/sanitize.py"
-    timeout 900 compute-sanitizer --tool $tool python tools/sanitize.py 2>&1 | grep -E "^ok|ERROR SUMMARY|=========.*(Invalid|Barrier|Uninitialized|error)" | head -80
+    timeout ${AW_SANITIZE_TIMEOUT:-900} compute-sanitizer --tool $tool python tools/sanitize.py 2>&1 | grep -E "^ok|ERROR SUMMARY|=========.*(Invalid|Barrier|Uninitialized|error)" | head -80
   done
   echo; echo "## compute-sanitizer --tool racecheck python tools/sanitize_small.py"
-  timeout 900 compute-sanitizer --tool racecheck python tools/sanitize_small.py 2>&1 | grep -E "^ok|ERROR SUMMARY|RACECHECK SUMMARY|=========.*(hazard|Race|error)" | head -60
+  timeout ${AW_SANITIZE_TIMEOUT:-900} compute-sanitizer --tool racecheck python tools/sanitize_small.py 2>&1 | grep -E "^ok|ERROR SUMMARY|RACECHECK SUMMARY|=========.*(hazard|Race|error)" | grep -v "     and \(Write\|Read\) access" | head -120
 } > $OUT 2>&1
 tail -5 $OUT
